@@ -1,0 +1,107 @@
+"""ctypes binding of libarx_b200.so (the C ABI declared in include/arx_b200.h).
+
+The product path fails loudly when the CUDA library is missing or a call returns an
+error code: there is no CPU fallback anywhere in this package.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libarx_b200.so')
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+c_f32p = ctypes.POINTER(ctypes.c_float)
+vp = ctypes.c_void_p
+
+
+class AttrDesc(ctypes.Structure):
+    """arx_attr_desc (include/arx_b200.h)."""
+    _fields_ = [('table', vp), ('table_acc', vp), ('bias', vp), ('bias_acc', vp),
+                ('values', vp), ('starts', vp), ('lengths', vp), ('touch', vp),
+                ('vocab', ctypes.c_int64), ('kind', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class BwdPlan(ctypes.Structure):
+    """arx_bwd_plan (include/arx_b200.h)."""
+    _fields_ = [('counters', vp), ('uniq_tok', vp), ('uniq_attr', vp), ('row_base', vp),
+                ('row_cnt', vp), ('bucket_src', vp), ('bucket_w', vp),
+                ('cap_rows', ctypes.c_int64), ('cap_occ', ctypes.c_int64)]
+
+
+POOL_MEAN, POOL_CONCAT = 0, 1
+OPT_ADAGRAD, OPT_SGD, OPT_NONE = 0, 1, 2
+LOSS_KIND = {'ce': 0, 'warp': 1, 'warp_eval': 1, 'rs': 2, 'rs-sig': 3, 'rs-sig2': 4, 'bbpr': 5, 'mw': 6}
+LOSS_FUNC = {'log': 0, 'exp': 1, 'poly': 2, 'poly2': 3, 'linear': 4, 'square': 5}
+
+i64, i32, f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes; every function returns int except the two info calls.
+SIGNATURES = {
+    'arx_pool_fwd': [vp, i32, i32, vp, i64, vp, i64, i32, vp, vp],
+    'arx_mulhot_flat_index': [vp, i32, vp, i64, vp, vp, vp, vp],
+    'arx_bwd_plan_begin': [BwdPlan, vp],
+    'arx_bwd_plan_count': [vp, i32, i32, vp, i64, BwdPlan, vp],
+    'arx_bwd_plan_alloc': [vp, BwdPlan, vp],
+    'arx_bwd_plan_fill': [vp, i32, i32, vp, i64, i32, i64, BwdPlan, vp],
+    'arx_bwd_plan_end': [vp, BwdPlan, vp],
+    'arx_pool_bwd_plan': [vp, i32, vp, i64, i32, BwdPlan, vp],
+    'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
+    'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, vp],
+    'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
+    'arx_loss_rows': [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
+    'arx_rowdot_fwd': [vp, vp, vp, i64, i32, vp, vp],
+    'arx_rowdot_bwd': [vp, vp, vp, i64, i32, vp, vp, vp],
+    'arx_topk_rows': [vp, i64, i64, i64, i32, vp, vp, vp],
+    'arx_dense_update': [vp, vp, vp, i64, f32, vp, i32, vp],
+    'arx_scale_mask': [vp, vp, f32, i64, vp, vp],
+}
+
+_ERR = {-1: 'ARX_E_BADARG', -2: 'ARX_E_LAUNCH', -3: 'ARX_E_UNSUPPORTED', -4: 'ARX_E_CAPACITY'}
+
+_lib = None
+launch_count = 0   # number of C-ABI compute calls issued (bench.py's gpu_launches evidence)
+
+
+def load():
+    """dlopen the in-tree library; raises (never falls back) if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RuntimeError('libarx_b200.so not built: run `python -c "import __graft_entry__ as g; '
+                           'g.build()"` or `make -C a-recsys_b200/csrc` (expected at %s)' % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    lib.arx_abi_version.argtypes = []
+    lib.arx_abi_version.restype = ctypes.c_int
+    lib.arx_build_info.argtypes = []
+    lib.arx_build_info.restype = ctypes.c_char_p
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on torch's current stream; raise on any error code."""
+    global launch_count
+    lib = load()
+    rc = getattr(lib, name)(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        raise RuntimeError('%s failed: %s (%d)' % (name, _ERR.get(rc, '?'), rc))
+    return rc

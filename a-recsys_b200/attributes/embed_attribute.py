@@ -1,0 +1,587 @@
+"""EmbeddingAttribute on B200: same public surface as the reference class
+(attributes/embed_attribute.py:19-747) — get_batch_user / get_batch_item / get_prediction /
+get_target_score / get_sampled_item / compute_loss / get_warp_mask / prepare_warp /
+target_mapping / add_input / get_user_model_size / get_item_model_size — executed eagerly by
+the sm_100a kernels of libarx_b200.so instead of a TF-1 graph.
+
+Differences that are deliberate:
+  * placeholders become device index tensors filled by add_input();
+  * catalog scoring pools the catalog first and then contracts (pooling is linear), the
+    literal "score tokens, then pool" order lives only in the oracle;
+  * the dense bool mask Variable [mb*V] (:651-672) becomes a per-user CSR of positives;
+  * backward is explicit: every lookup registers its output gradient with
+    `push_grad`, and `apply_gradients` de-duplicates all touched rows of a table set and
+    applies Adagrad once per row (TF sums duplicate indices before the sparse apply).
+There is no CPU path: constructing this class without CUDA raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import AttrDesc, BwdPlan, POOL_MEAN, POOL_CONCAT, OPT_ADAGRAD, OPT_SGD, OPT_NONE, call, ptr
+
+ADAGRAD_INIT_ACC = 0.1     # tf.train.AdagradOptimizer(initial_accumulator_value=0.1)
+
+
+class _TableSet(object):
+    """All tables of one variable prefix ('user' | 'item' | 'item_output') plus the device
+    descriptor array the kernels read."""
+
+    def __init__(self, owner, prefix, att, att_dev, with_bias):
+        self.prefix = prefix
+        self.att = att
+        self.n_cat = att.num_features_cat
+        self.n_mul = att.num_features_mulhot
+        self.n_attr = self.n_cat + self.n_mul
+        self.with_bias = with_bias
+        self.names, self.bias_names = [], []
+        descs = (AttrDesc * self.n_attr)()
+        feats_cat, feats_mul, starts, lengths = att_dev
+        k = 0
+        for kind, cnt in ((0, self.n_cat), (1, self.n_mul)):
+            for i in range(cnt):
+                tag = 'cat' if kind == 0 else 'mulhot'
+                name = '%sembed_%s_%d' % (prefix, tag, i)
+                bname = '%s_bias_%s_%d' % (prefix, tag, i)
+                d = descs[k]
+                d.table = owner.params[name].data_ptr()
+                d.table_acc = owner.accs[name].data_ptr()
+                if with_bias:
+                    d.bias = owner.params[bname].data_ptr()
+                    d.bias_acc = owner.accs[bname].data_ptr()
+                d.values = (feats_cat[i] if kind == 0 else feats_mul[i]).data_ptr()
+                if kind == 1:
+                    d.starts = starts[i].data_ptr()
+                    d.lengths = lengths[i].data_ptr()
+                d.touch = owner.touch[name].data_ptr()
+                d.vocab = owner.params[name].shape[0]
+                d.kind = kind
+                self.names.append(name)
+                self.bias_names.append(bname if with_bias else None)
+                k += 1
+        raw = np.frombuffer(bytes(descs), dtype=np.uint8).copy()
+        self.descs_dev = torch.from_numpy(raw).to(owner.device)
+        self.desc_size = ctypes.sizeof(AttrDesc)
+        self.total_vocab = sum(owner.params[n].shape[0] for n in self.names)
+        self.max_len = [1] * self.n_cat + [int(att.mulhot_lengths[i].max()) for i in range(self.n_mul)]
+        self.pending = []          # (attr_begin, n_attr, ids, mode, dout[n, w], dbias or None, plan_key)
+        self.plans = {}            # plan_key -> (_Plan, rows)
+
+    def desc_ptr(self, attr_begin=0):
+        return self.descs_dev.data_ptr() + attr_begin * self.desc_size
+
+    def attr_range(self, no_id=False, no_attribute=False):
+        """embed_attribute.py:356-373: no_id drops categorical attribute 0, no_attribute keeps it only."""
+        if no_attribute:
+            return 0, 1
+        if no_id:
+            return 1, self.n_attr - 1
+        return 0, self.n_attr
+
+
+class _Plan(object):
+    """Device buffers of one arx_bwd_plan."""
+
+    def __init__(self, device, cap_rows, cap_occ):
+        i32 = dict(dtype=torch.int32, device=device)
+        self.counters = torch.zeros(8, **i32)
+        self.uniq_tok = torch.empty(cap_rows, **i32)
+        self.uniq_attr = torch.empty(cap_rows, **i32)
+        self.row_base = torch.empty(cap_rows, **i32)
+        self.row_cnt = torch.empty(cap_rows, **i32)
+        self.bucket_src = torch.empty(cap_occ, **i32)
+        self.bucket_w = torch.empty(cap_occ, dtype=torch.float32, device=device)
+        self.cap_rows, self.cap_occ = cap_rows, cap_occ
+        self.c = BwdPlan(self.counters.data_ptr(), self.uniq_tok.data_ptr(), self.uniq_attr.data_ptr(),
+                         self.row_base.data_ptr(), self.row_cnt.data_ptr(), self.bucket_src.data_ptr(),
+                         self.bucket_w.data_ptr(), cap_rows, cap_occ)
+
+
+class EmbeddingAttribute(object):
+    def __init__(self, user_attributes, item_attributes, mb, n_sampled, input_steps=0,
+                 item_output=False, item_ind2logit_ind=None, logit_ind2item_ind=None,
+                 indices_item=None, devices=['/gpu:0'], device=None, seed=None, params=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError('arecsys_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        _lib.load()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.user_attributes = user_attributes
+        self.item_attributes = item_attributes
+        self.batch_size = mb
+        self.n_sampled = n_sampled
+        self.input_steps = input_steps
+        self.item_output = item_output
+        self.num_item_features = item_attributes.num_features_cat + item_attributes.num_features_mulhot
+        self.item_ind2logit_ind = item_ind2logit_ind
+        self.logit_ind2item_ind = logit_ind2item_ind
+        if logit_ind2item_ind is not None:
+            self.logit_size = len(logit_ind2item_ind)
+        self.indices_item = indices_item if indices_item is not None else range(getattr(self, 'logit_size', 0))
+        self.devices = devices
+        self.mask, self.pos_indices = {}, {}
+        ua, ia = user_attributes, item_attributes
+        sizes = set(ua._embedding_size_list_cat + ua._embedding_size_list_mulhot +
+                    ia._embedding_size_list_cat + ia._embedding_size_list_mulhot)
+        assert len(sizes) == 1, 'all attribute embeddings share one size (set_model_size(int))'
+        self.dim = sizes.pop()
+
+        # ---- attribute arrays -> HBM (embed_attribute.py:308-318) ------------------------
+        self.att = {'user': self._init_attributes(ua), 'item': self._init_attributes(ia)}
+        if item_output:
+            self.att['item_output'] = self.att['item']
+
+        # ---- variables (embed_attribute.py:265-306) --------------------------------------
+        gen = torch.Generator(device='cpu')
+        gen.manual_seed(0 if seed is None else seed)
+        self.params, self.accs, self.touch = {}, {}, {}
+        self._embedded(ua, 'user', gen, params)
+        self._embedded(ia, 'item', gen, params)
+        self._embedded_bias(ia, 'item', gen, params)
+        if item_output:
+            self._embedded(ia, 'item_output', gen, params)
+            self._embedded_bias(ia, 'item_output', gen, params)
+        self.sets = {'user': _TableSet(self, 'user', ua, self.att['user'], False),
+                     'item': _TableSet(self, 'item', ia, self.att['item'], True)}
+        if item_output:
+            self.sets['item_output'] = _TableSet(self, 'item_output', ia, self.att['item'], True)
+
+        # ---- feeds (placeholders in the reference, :72-93) -------------------------------
+        self.u_indices, self.i_indices = {}, {}
+        # catalog ids in logit order (the 'full' constants of :97-108 in CSR form)
+        if logit_ind2item_ind is not None:
+            V = self.logit_size
+            ids = np.asarray([logit_ind2item_ind[v] for v in range(V)], dtype=np.int32) \
+                if not isinstance(logit_ind2item_ind, np.ndarray) else logit_ind2item_ind.astype(np.int32)
+            self.catalog_ids = torch.from_numpy(ids).to(self.device)
+            n_items = ia.num_entities
+            if hasattr(item_ind2logit_ind, 'as_array'):
+                i2l = item_ind2logit_ind.as_array(n_items - 1)
+            else:
+                i2l = np.full(n_items, -1, dtype=np.int32)
+                i2l[ids] = np.arange(V, dtype=np.int32)
+            self.item2logit_dev = torch.from_numpy(i2l).to(self.device)
+        self.sampled_ids = None
+        self.sampled_pos_dev = None
+        self.pos_csr = {}          # (kind) -> (ptr, idx) per-user positives, device
+        self.pos_item_set = None
+        self.pos_item_set_eval = None
+
+    # ------------------------------------------------------------------ construction --
+    def _init_attributes(self, att):
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        return ([t(a) for a in att.features_cat], [t(a) for a in att.features_mulhot],
+                [t(a) for a in att.mulhot_starts], [t(a) for a in att.mulhot_lengths])
+
+    def _new_var(self, name, shape, gen, params):
+        if params is not None and name in params:
+            w = torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).reshape(shape).clone()
+        else:
+            # tf.get_variable default in TF1.0: glorot_uniform; unseeded there.
+            limit = math.sqrt(6.0 / (shape[0] + shape[1]))
+            w = (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * limit
+        self.params[name] = w.to(self.device).contiguous()
+        self.accs[name] = torch.full(shape, ADAGRAD_INIT_ACC, dtype=torch.float32, device=self.device)
+
+    def _embedded(self, att, prefix, gen, params):
+        for tag, n, V in (('cat', att.num_features_cat, att._embedding_classes_list_cat),
+                          ('mulhot', att.num_features_mulhot, att._embedding_classes_list_mulhot)):
+            for i in range(n):
+                name = '%sembed_%s_%d' % (prefix, tag, i)
+                self._new_var(name, (V[i], self.dim), gen, params)
+                self.touch[name] = torch.zeros(V[i], dtype=torch.int32, device=self.device)
+
+    def _embedded_bias(self, att, prefix, gen, params):
+        for tag, n, V in (('cat', att.num_features_cat, att._embedding_classes_list_cat),
+                          ('mulhot', att.num_features_mulhot, att._embedding_classes_list_mulhot)):
+            for i in range(n):
+                self._new_var('%s_bias_%s_%d' % (prefix, tag, i), (V[i], 1), gen, params)
+
+    # ------------------------------------------------------------------ lookups -------
+    def _ids(self, x):
+        if isinstance(x, torch.Tensor):
+            return x.to(device=self.device, dtype=torch.int32).contiguous()
+        return torch.as_tensor(np.asarray(x, dtype=np.int32)).to(self.device, non_blocking=True)
+
+    def pool(self, prefix, ids, mode=POOL_MEAN, want_bias=False, no_id=False, no_attribute=False,
+             out=None, bias_out=None):
+        """K1+K2 over `ids` for the table set `prefix`.  Returns (out, bias, (attr_begin, n_attr))."""
+        ts = self.sets[prefix]
+        a0, na = ts.attr_range(no_id, no_attribute)
+        n = ids.numel()
+        width = self.dim if mode == POOL_MEAN else self.dim * na
+        if out is None:
+            out = torch.empty((n, width), dtype=torch.float32, device=self.device)
+        if want_bias and bias_out is None:
+            bias_out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        call('arx_pool_fwd', ts.desc_ptr(a0), na, self.dim, ids.data_ptr(), n, out.data_ptr(),
+             out.stride(0), mode, ptr(bias_out) if want_bias else None)
+        return out, (bias_out if want_bias else None), (a0, na)
+
+    def flat_indices(self, prefix, attr, ids):
+        """Integer part of K2 (mulhot_index.py:48-67): (flat token index, segment ids)."""
+        ts = self.sets[prefix]
+        ids = self._ids(ids)
+        f = attr - ts.n_cat
+        lens = self.att[prefix][3][f][ids.long()].long() if attr >= ts.n_cat else torch.ones_like(ids).long()
+        offs = torch.zeros(ids.numel() + 1, dtype=torch.int64, device=self.device)
+        offs[1:] = torch.cumsum(lens, 0)
+        total = int(offs[-1].item())
+        flat = torch.empty(total, dtype=torch.int32, device=self.device)
+        seg = torch.empty(total, dtype=torch.int32, device=self.device)
+        call('arx_mulhot_flat_index', ts.desc_ptr(0), attr, ids.data_ptr(), ids.numel(), offs.data_ptr(),
+             flat.data_ptr(), seg.data_ptr())
+        return flat, seg
+
+    # -- embed_attribute.py:222-237 --------------------------------------------------------
+    def get_batch_user(self, keep_prob, concat=True, no_id=False, device='/gpu:0', dropout_mask=None,
+                       u_inds=None):
+        ua = self.user_attributes
+        ids = self.u_indices['input'] if u_inds is None else self._ids(u_inds)
+        if no_id and ua.num_features_cat == 1:                         # :356-366
+            z = torch.zeros((ids.numel(), self.dim), dtype=torch.float32, device=self.device)
+            self._last_user = None
+            return z, None
+        mode = POOL_CONCAT if concat else POOL_MEAN
+        out, _, rng = self.pool('user', ids, mode, False, no_id=no_id)
+        self._last_user = ('user', rng, ids, mode)
+        out = self.dropout(out, keep_prob, dropout_mask)               # :236
+        return out, None
+
+    def dropout(self, x, keep_prob, mask=None):
+        """tf.nn.dropout: x / keep * floor(keep + U[0,1)); identity at keep_prob == 1."""
+        if keep_prob == 1.0:
+            return x
+        if mask is None:
+            mask = torch.floor(torch.rand_like(x) + keep_prob)
+        y = torch.empty_like(x)
+        call('arx_scale_mask', x.data_ptr(), mask.data_ptr(), 1.0 / keep_prob, x.numel(), y.data_ptr())
+        self._last_dropout_mask = mask
+        return y
+
+    # -- embed_attribute.py:239-254 --------------------------------------------------------
+    def get_batch_item(self, name, batch_size, concat=False, keep_prob=1.0, no_attribute=False,
+                       device='/gpu:0', reduce=None):
+        """reduce=None mirrors the reference (list of per-attribute tensors, or the concat);
+        reduce='mean' returns the fused mean over attributes directly."""
+        assert name in self.i_indices
+        assert keep_prob == 1.0, 'otherwise not implemented'
+        ids = self.i_indices[name]
+        if reduce == 'mean':
+            out, b, rng = self.pool('item', ids, POOL_MEAN, True, no_attribute=no_attribute)
+            return out, b
+        out, b, (a0, na) = self.pool('item', ids, POOL_CONCAT, True, no_attribute=no_attribute)
+        if concat:
+            return out, b
+        return [out[:, f * self.dim:(f + 1) * self.dim] for f in range(na)], b
+
+    def get_sampled_item(self, n_sampled, device='/gpu:0'):
+        """embed_attribute.py:256-263 (unused by HMF)."""
+        out, b, _ = self.pool('item', self.sampled_ids, POOL_MEAN, True)
+        return out, b
+
+    # -- embed_attribute.py:320-348 --------------------------------------------------------
+    def pass_sampled_items(self, item_sampled):
+        """`update_sampled`: remember the sampled pool (its CSR is read straight from the
+        attribute store by the kernels, no materialisation) and the item -> pool-position map."""
+        self.sampled_ids = self._ids(item_sampled)
+        n_items = self.item_attributes.num_entities
+        if self.sampled_pos_dev is None:
+            self.sampled_pos_dev = torch.full((n_items,), -1, dtype=torch.int32, device=self.device)
+        else:
+            self.sampled_pos_dev.fill_(-1)
+        self.sampled_pos_dev[self.sampled_ids.long()] = torch.arange(
+            self.sampled_ids.numel(), dtype=torch.int32, device=self.device)
+        self._sampled_version = getattr(self, '_sampled_version', 0) + 1
+        for k in ('mw_train', 'mw_eval'):
+            self.pos_csr.pop(k, None)
+        for ts in self.sets.values():
+            ts.plans.pop('sampled', None)
+
+    # -- pooled catalog (the rewritten K3) ---------------------------------------------------
+    def _out_prefix(self):
+        return 'item_output' if self.item_output else 'item'
+
+    def pool_catalog(self, pool='full', output_feat=1):
+        ids = self.catalog_ids if pool == 'full' else self.sampled_ids
+        P, beta, _ = self.pool(self._out_prefix(), ids, POOL_MEAN, True, no_attribute=(output_feat == 0))
+        return P, beta, ids
+
+    # -- embed_attribute.py:148-206 --------------------------------------------------------
+    def get_prediction(self, latent, pool='full', device='/gpu:0', output_feat=1):
+        """logits [mb, V] (or [mb, S]).  output_feat 0 (id only) and 1 (mean pooling) are linear
+        in the tables and use the pool-first form; 2/3 (max / log-sum-exp pooling) are not
+        implemented on the CUDA path yet."""
+        if output_feat not in (0, 1):
+            print('Error: Attribute combination not implemented!')
+            exit(1)
+        if isinstance(latent, list):
+            raise NotImplementedError('per-attribute latent lists are not supported on the CUDA path')
+        P, beta, ids = self.pool_catalog(pool, output_feat)
+        mb, N = latent.shape[0], P.shape[0]
+        logits = torch.empty((mb, N), dtype=torch.float32, device=self.device)
+        call('arx_gemm', latent.data_ptr(), P.data_ptr(), logits.data_ptr(), mb, N, self.dim, 0, 1,
+             beta.data_ptr(), 1.0, 0.0)
+        self._last_pred = (latent, P, beta, ids, pool, output_feat)
+        return logits
+
+    # -- embed_attribute.py:208-220 --------------------------------------------------------
+    def get_target_score(self, latent, inds, device='/gpu:0'):
+        ids = self._ids(inds)
+        Pt, bt, _ = self.pool(self._out_prefix(), ids, POOL_MEAN, True)
+        out = torch.empty((ids.numel(),), dtype=torch.float32, device=self.device)
+        call('arx_rowdot_fwd', latent.data_ptr(), Pt.data_ptr(), bt.data_ptr(), ids.numel(), self.dim,
+             out.data_ptr())
+        self._last_target = (latent, Pt, ids)
+        return out
+
+    # -- embed_attribute.py:510-523 --------------------------------------------------------
+    def get_user_model_size(self, no_id=False, concat=True):
+        ua = self.user_attributes
+        if concat:
+            cat_start = 1 if no_id else 0
+            return (sum(ua._embedding_size_list_cat[cat_start:ua.num_features_cat]) +
+                    sum(ua._embedding_size_list_mulhot[0:ua.num_features_mulhot]))
+        return ua._embedding_size_list_cat[0]
+
+    def get_item_model_size(self, concat=True):
+        ia = self.item_attributes
+        if concat:
+            return (sum(ia._embedding_size_list_cat[0:ia.num_features_cat]) +
+                    sum(ia._embedding_size_list_mulhot[0:ia.num_features_mulhot]))
+        return ia._embedding_size_list_cat[0]
+
+    # -- embed_attribute.py:525-649 --------------------------------------------------------
+    def compute_loss(self, logits, item_target, loss='ce', true_rank=False, loss_func='log',
+                     exp_p=1.005, device='/gpu:0', row_scale=None, want_grad=True, pos_rows=None,
+                     forward_only=False):
+        """Per-row loss [mb].  With want_grad the gradient d(sum_b row_scale_b * loss_b)/d logits
+        overwrites `logits` in place (the scores are not needed afterwards) and, for 'mw',
+        d/d target-score is returned through self._last_dtarget."""
+        assert loss in ['ce', 'mce', 'warp', 'warp_eval', 'rs', 'rs-sig', 'rs-sig2', 'mw', 'bbpr',
+                        'bpr', 'bpr-hinge']
+        if loss in ('mce', 'bpr', 'bpr-hinge'):
+            # 'mce' has no branch in the reference (:527 vs :529-549); bpr/bpr-hinge inputs are
+            # never fed there (embed_attribute.py:704-706 commented out).
+            print('Error: not implemented other loss!!')
+            exit(1)
+        mb, V = logits.shape
+        out = torch.empty((mb,), dtype=torch.float32, device=self.device)
+        tgt = ts = None
+        if loss == 'mw':
+            ts = item_target
+        else:
+            tgt = item_target if isinstance(item_target, torch.Tensor) else self._ids(item_target)
+        pos_row = pos_ptr = pos_idx = None
+        if loss != 'ce':
+            key = ('mw' if loss == 'mw' else 'full') + ('_eval' if forward_only else '_train')
+            pos_ptr, pos_idx = self._positives(key)
+            pos_row = pos_rows if pos_rows is not None else self.u_indices['input']
+        rank = torch.empty((mb,), dtype=torch.int64, device=self.device) if (true_rank or loss == 'warp_eval') else None
+        dts = torch.empty((mb,), dtype=torch.float32, device=self.device) if (loss == 'mw' and want_grad) else None
+        call('arx_loss_rows', logits.data_ptr(), mb, V, logits.stride(0), ptr(tgt), ptr(ts), ptr(pos_row),
+             ptr(pos_ptr), ptr(pos_idx), _lib.LOSS_KIND[loss], _lib.LOSS_FUNC[loss_func], float(exp_p),
+             ptr(row_scale), out.data_ptr(), logits.data_ptr() if want_grad else None, ptr(dts), ptr(rank))
+        self._last_dtarget = dts
+        if loss == 'warp_eval' or true_rank:
+            return [out, rank]
+        return out
+
+    # -- positives: embed_attribute.py:651-677, :721-747 -------------------------------------
+    def get_warp_mask(self, device='/gpu:0'):
+        """The reference returns scatter_update ops on a dense bool Variable; here the mask is the
+        per-user CSR consumed inside the loss kernel, so there is nothing to run."""
+        self.set_mask, self.reset_mask = {}, {}
+        return self.set_mask, self.reset_mask
+
+    def prepare_warp(self, pos_item_set, pos_item_set_eval):
+        self.pos_item_set = pos_item_set
+        self.pos_item_set_eval = pos_item_set_eval
+        self.pos_csr = {}
+        self._pos_host = {}
+
+    def _positives_host(self, which):
+        """CSR over users of positive ITEM indices (host, int32), built once per item set."""
+        if which in self._pos_host:
+            return self._pos_host[which]
+        item_set = self.pos_item_set_eval if which == 'eval' else self.pos_item_set
+        n_users = self.user_attributes.num_entities
+        if isinstance(item_set, tuple):          # already CSR (ptr, items) — large synthetic sets
+            ptr_, items = item_set
+        else:
+            lens = np.zeros(n_users, dtype=np.int64)
+            for u, v in item_set.items():
+                lens[u] = len(v)
+            ptr_ = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+            items = np.empty(int(ptr_[-1]), dtype=np.int32)
+            for u, v in item_set.items():
+                items[ptr_[u]:ptr_[u + 1]] = np.fromiter(v, dtype=np.int32, count=len(v))
+        self._pos_host[which] = (np.asarray(ptr_, dtype=np.int32), np.asarray(items, dtype=np.int32))
+        return self._pos_host[which]
+
+    def _positives(self, key):
+        """Device CSR (ptr, idx) for key in {full,mw}_{train,eval}: idx are masked COLUMN ids —
+        logit indices (sorted per user) for the full losses, sampled-pool positions (or -1) for mw."""
+        if key in self.pos_csr:
+            return self.pos_csr[key]
+        kind, which = key.split('_')
+        ptr_h, items_h = self._positives_host(which)
+        ptr_d = torch.from_numpy(ptr_h).to(self.device)
+        items_d = torch.from_numpy(items_h).to(self.device).long()
+        if kind == 'full':
+            cols = self.item2logit_dev[items_d]
+            # sort columns inside each user's slice: one global sort on (user, col) keys
+            seg = torch.repeat_interleave(torch.arange(len(ptr_h) - 1, device=self.device),
+                                          (ptr_d[1:] - ptr_d[:-1]).long())
+            keyv = seg * (int(self.logit_size) + 1) + (cols.long() + 1)
+            cols = cols[torch.argsort(keyv)]
+        else:
+            cols = self.sampled_pos_dev[items_d]
+        self.pos_csr[key] = (ptr_d, cols.to(torch.int32).contiguous())
+        return self.pos_csr[key]
+
+    # -- embed_attribute.py:679-684 --------------------------------------------------------
+    def target_mapping(self, item_target):
+        m = self.item_ind2logit_ind
+        target = []
+        for items in item_target:
+            if isinstance(items, torch.Tensor):
+                target.append(self.item2logit_dev[items.long()])
+            elif isinstance(items, np.ndarray) and hasattr(m, 'as_array'):
+                target.append(items)
+            else:
+                target.append([m[v] for v in items])
+        return target
+
+    # -- embed_attribute.py:697-747 --------------------------------------------------------
+    def add_input(self, input_feed, user_input, item_input, neg_item_input=None, item_sampled=None,
+                  item_sampled_id2idx=None, forward_only=False, recommend=False, loss=None):
+        """Feed the 'placeholders'.  Returns the reference's triple; the sampled-pool refresh is
+        performed right here (it was a separate session.run in hmf_model.py:206-207)."""
+        if self.user_attributes is not None:
+            self.u_indices['input'] = self._ids(user_input)
+        if self.item_attributes is not None and self.input_steps > 0 and item_input is not None:
+            for step in range(len(item_input)):
+                self.i_indices['input{}'.format(step)] = self._ids(item_input[step])
+        update_sampled = []
+        if (self.item_attributes is not None and recommend is False and item_sampled is not None
+                and loss in ['mw', 'mce']):
+            self.pass_sampled_items(item_sampled)
+            update_sampled = ['update_sampled']
+        return update_sampled, {}, {}
+
+    # ------------------------------------------------------------------ backward ------
+    def push_grad(self, prefix, rng, ids, mode, dout, dbias=None, plan_key=None):
+        """Register d(loss)/d(pooled output) of one lookup (the IndexedSlices of tf.gradients)."""
+        a0, na = rng
+        self.sets[prefix].pending.append((a0, na, ids, mode, dout, dbias, plan_key))
+
+    def _plan_for(self, ts, entries):
+        """Build (or fetch the cached) backward plan for the pending lookups of one table set."""
+        single_key = entries[0][6] if len(entries) == 1 else None
+        if single_key is not None and single_key in ts.plans:
+            return ts.plans[single_key]
+        cap_occ = 0
+        for (a0, na, ids, mode, dout, dbias, key) in entries:
+            cap_occ += int(ids.numel()) * sum(ts.max_len[a0:a0 + na])
+        if single_key == 'catalog':
+            ia = self.item_attributes     # exact: the catalog CSR is static
+            cap_occ = int(ids.numel()) * ts.n_cat + sum(len(v) for v in ia.full_values_tr)
+        cap_occ = max(cap_occ, 1)
+        cap_rows = max(min(cap_occ, ts.total_vocab), 1)
+        plan = _Plan(self.device, cap_rows, cap_occ) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
+        call('arx_bwd_plan_begin', plan.c)
+        for (a0, na, ids, mode, dout, dbias, key) in entries:
+            call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
+        call('arx_bwd_plan_alloc', ts.desc_ptr(0), plan.c)
+        row = 0
+        for (a0, na, ids, mode, dout, dbias, key) in entries:
+            call('arx_bwd_plan_fill', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), mode, row, plan.c)
+            row += ids.numel() * (na if mode == POOL_CONCAT else 1)
+        call('arx_bwd_plan_end', ts.desc_ptr(0), plan.c)
+        if single_key is not None:
+            ts.plans[single_key] = plan
+        return plan
+
+    def _scratch_plan(self, ts, cap_rows, cap_occ):
+        p = getattr(ts, '_scratch', None)
+        if p is None or p.cap_rows < cap_rows or p.cap_occ < cap_occ:
+            p = _Plan(self.device, cap_rows, cap_occ)
+            ts._scratch = p
+        return p
+
+    def _arena(self, entries):
+        """Row arena [R, dim] (+ aligned bias grads [R]) of the pending lookups."""
+        rows, biases, any_bias = [], [], any(e[5] is not None for e in entries)
+        for (a0, na, ids, mode, dout, dbias, key) in entries:
+            r = dout.reshape(-1, self.dim) if mode == POOL_CONCAT else dout
+            rows.append(r)
+            if any_bias:
+                if dbias is None:
+                    biases.append(torch.zeros(r.shape[0], dtype=torch.float32, device=self.device))
+                else:
+                    # the pooled bias is always the MEAN over attributes (:412), also in concat mode
+                    biases.append((dbias / na).repeat_interleave(na) if mode == POOL_CONCAT else dbias)
+        if len(rows) == 1:
+            arena = rows[0] if rows[0].is_contiguous() else rows[0].contiguous()
+            bias = biases[0].contiguous() if any_bias else None
+        else:
+            arena = torch.cat(rows, 0)
+            bias = torch.cat(biases, 0) if any_bias else None
+        return arena, bias
+
+    def sparse_sumsq(self, out):
+        """Add sum over IndexedSlices values of g^2 (clip_by_global_norm term) into out[0]."""
+        for ts in self.sets.values():
+            if not ts.pending:
+                continue
+            plan = self._plan_for(ts, ts.pending)
+            arena, bias = self._arena(ts.pending)
+            ts._ready = (plan, arena, bias)
+            call('arx_pool_bwd_sumsq', ts.desc_ptr(0), self.dim, plan.c, arena.data_ptr(), arena.stride(0),
+                 ptr(bias), out.data_ptr())
+
+    def apply_gradients(self, lr, opt=OPT_ADAGRAD, grad_scale=None):
+        """De-duplicated sparse optimizer step on every table set with pending gradients
+        (hmf_model.py:146-151; lstm/seqModel.py:173-182)."""
+        for ts in self.sets.values():
+            if not ts.pending:
+                continue
+            ready = getattr(ts, '_ready', None)
+            if ready is not None:
+                plan, arena, bias = ready
+                ts._ready = None
+            else:
+                plan = self._plan_for(ts, ts.pending)
+                arena, bias = self._arena(ts.pending)
+            call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
+                 arena.stride(0), ptr(bias), float(lr), ptr(grad_scale), opt, None, None)
+            ts.pending = []
+
+    def row_gradients(self, prefix):
+        """Oracle check: dense gradients of every table of `prefix` from the pending lookups,
+        through the same plan + segment-reduce kernels (ARX_OPT_NONE).  Clears the pending list."""
+        ts = self.sets[prefix]
+        plan = self._plan_for(ts, ts.pending)
+        arena, bias = self._arena(ts.pending)
+        nu = int(plan.counters[0].item())
+        assert int(plan.counters[2].item()) == 0, 'backward plan capacity exceeded'
+        rows = torch.zeros((max(nu, 1), self.dim), dtype=torch.float32, device=self.device)
+        brow = torch.zeros((max(nu, 1),), dtype=torch.float32, device=self.device)
+        call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
+             arena.stride(0), ptr(bias), 0.0, None, OPT_NONE, rows.data_ptr(), brow.data_ptr())
+        grads = {n: torch.zeros_like(self.params[n]) for n in ts.names}
+        bgrads = {n: torch.zeros_like(self.params[n]) for n in ts.bias_names if n}
+        tok = plan.uniq_tok[:nu].long()
+        attr = plan.uniq_attr[:nu].long()
+        for f, name in enumerate(ts.names):
+            sel = attr == f
+            grads[name][tok[sel]] = rows[:nu][sel]
+            if ts.bias_names[f] and bias is not None:
+                bgrads[ts.bias_names[f]][tok[sel], 0] = brow[:nu][sel]
+        ts.pending = []
+        grads.update(bgrads)
+        return grads

@@ -1,0 +1,305 @@
+"""Hybrid matrix factorisation (HMF) on B200 — same constructor, attributes and step()
+protocol as the reference LatentProductModel (hmf/hmf_model.py:19-260), executed eagerly
+through libarx_b200.so.
+
+user vector = mean of attribute embeddings (K1+K2) -> dropout -> (optional 2-layer MLP, K7)
+-> catalog scores (K3: pooled catalog then U*P^T) -> loss (K5/K6) -> explicit backward ->
+de-duplicated sparse Adagrad on every touched table row (K2b) + dense Adagrad on the MLP.
+"""
+import os
+import random
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import POOL_MEAN, OPT_ADAGRAD, call, ptr
+from ..attributes import embed_attribute
+
+_FULL_LOSSES = ['warp', 'ce', 'rs', 'rs-sig', 'rs-sig2', 'bbpr']
+_MASKED = ['warp', 'warp_eval', 'mw', 'rs', 'rs-sig', 'rs-sig2', 'bbpr']
+
+
+class _Var(object):
+    """Stand-in for a non-trainable tf.Variable scalar (learning_rate, global_step)."""
+
+    def __init__(self, v):
+        self.v = v
+
+    def eval(self, session=None):
+        return self.v
+
+    def assign(self, v):
+        self.v = v
+        return self
+
+
+class _Saver(object):
+    """tf.train.Saver(tf.global_variables()) equivalent (hmf_model.py:156): every table, bias,
+    Adagrad accumulator, MLP weight, learning rate and global step in one torch file."""
+
+    def __init__(self, model):
+        self.model = model
+
+    def save(self, sess, path, global_step=None, write_meta_graph=False):
+        m = self.model
+        if global_step is not None:
+            path = '%s-%d' % (path, global_step)
+        state = {'params': {k: v.cpu() for k, v in m.att_emb.params.items()},
+                 'accs': {k: v.cpu() for k, v in m.att_emb.accs.items()},
+                 'dense': {k: v.detach().cpu() for k, v in m.dense.items()},
+                 'dense_acc': {k: v.cpu() for k, v in m.dense_acc.items()},
+                 'learning_rate': m.learning_rate.eval(), 'global_step': m.global_step.eval()}
+        torch.save(state, path)
+        with open(os.path.join(os.path.dirname(path), 'checkpoint'), 'w') as f:
+            f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+        return path
+
+    def restore(self, sess, path):
+        m = self.model
+        state = torch.load(path, map_location='cpu')
+        for k, v in state['params'].items():
+            m.att_emb.params[k].copy_(v)
+        for k, v in state['accs'].items():
+            m.att_emb.accs[k].copy_(v)
+        for k, v in state['dense'].items():
+            m.dense[k].data.copy_(v)
+        for k, v in state['dense_acc'].items():
+            m.dense_acc[k].copy_(v)
+        m.learning_rate.assign(state['learning_rate'])
+        m.global_step.assign(state['global_step'])
+
+
+class LatentProductModel(object):
+    def __init__(self, user_size, item_size, size, num_layers, batch_size, learning_rate,
+                 learning_rate_decay_factor, user_attributes=None, item_attributes=None,
+                 item_ind2logit_ind=None, logit_ind2item_ind=None, loss_function='ce', GPU=None,
+                 logit_size_test=None, nonlinear=None, dropout=1.0, n_sampled=None, indices_item=None,
+                 dtype=torch.float32, top_N_items=100, hidden_size=500, loss_func='log',
+                 loss_exp_p=1.005, seed=None, params=None):
+        self.user_size = user_size
+        self.item_size = item_size
+        self.top_N_items = top_N_items
+        if user_attributes is not None:
+            user_attributes.set_model_size(size)
+            self.user_attributes = user_attributes
+        if item_attributes is not None:
+            item_attributes.set_model_size(size)
+            self.item_attributes = item_attributes
+        self.item_ind2logit_ind = item_ind2logit_ind
+        self.logit_ind2item_ind = logit_ind2item_ind
+        if logit_ind2item_ind is not None:
+            self.logit_size = len(logit_ind2item_ind)
+        self.indices_item = indices_item if indices_item is not None else range(self.logit_size)
+        self.logit_size_test = logit_size_test
+        self.nonlinear = nonlinear
+        self.loss_function = loss_function
+        self.n_sampled = n_sampled
+        self.batch_size = batch_size
+        self.size = size
+        self.loss_func = loss_func
+        self.loss_exp_p = loss_exp_p
+        if loss_function not in _FULL_LOSSES + ['warp_eval', 'mw']:
+            # bpr / bpr-hinge inputs are never fed in the reference (hmf_model.py:132-136 with
+            # embed_attribute.py:704-706 commented out); 'mce' has no loss branch.
+            print("not implemented!")
+            exit(-1)
+
+        self.learning_rate = _Var(float(learning_rate))
+        self._decay = learning_rate_decay_factor
+        self.learning_rate_decay_op = lambda: self.learning_rate.assign(self.learning_rate.eval() * self._decay)
+        self.global_step = _Var(0)
+        self.dropout = dropout
+        self.data_length = None
+        self.train_permutation = None
+        self.start_index = None
+
+        mb = batch_size
+        m = embed_attribute.EmbeddingAttribute(user_attributes, item_attributes, mb, self.n_sampled, 0,
+                                               False, item_ind2logit_ind, logit_ind2item_ind, seed=seed,
+                                               params=params)
+        self.att_emb = m
+        self.device = m.device
+        self.dense, self.dense_acc = {}, {}
+        if self.nonlinear in ['relu', 'tanh']:
+            gen = torch.Generator(device='cpu')
+            gen.manual_seed(1 if seed is None else seed + 1)
+            for name, shape in (('w1', (size, hidden_size)), ('b1', (hidden_size,)),
+                                ('w2', (hidden_size, size)), ('b2', (size,))):
+                if params is not None and name in params:
+                    w = torch.as_tensor(np.asarray(params[name]), dtype=torch.float32).reshape(shape).clone()
+                else:
+                    fan = shape[0] + (shape[1] if len(shape) > 1 else shape[0])
+                    lim = (6.0 / fan) ** 0.5
+                    w = (torch.rand(shape, generator=gen) * 2 - 1) * lim
+                self.dense[name] = w.to(self.device).requires_grad_(True)
+                self.dense_acc[name] = torch.full(shape, embed_attribute.ADAGRAD_INIT_ACC, device=self.device)
+        if loss_function in _MASKED:
+            self.set_mask, self.reset_mask = m.get_warp_mask()
+        self._row_scale = {}
+        self.saver = _Saver(self)
+
+    def prepare_warp(self, pos_item_set, pos_item_set_eval):
+        self.att_emb.prepare_warp(pos_item_set, pos_item_set_eval)
+
+    # ------------------------------------------------------------------ towers --------
+    def _scale(self, mb):
+        s = self._row_scale.get(mb)
+        if s is None:
+            s = torch.full((mb,), 1.0 / mb, dtype=torch.float32, device=self.device)
+            self._row_scale[mb] = s
+        return s
+
+    def _user_tower(self, keep_prob, masks):
+        """hmf_model.py:78-94.  Returns (u, ctx) where ctx lets _user_backward push dU back."""
+        m = self.att_emb
+        if self.nonlinear in ['relu', 'tanh']:
+            act = torch.relu if self.nonlinear == 'relu' else torch.tanh
+            u0, _ = m.get_batch_user(1.0, False)                              # :87
+            lookup = m._last_user
+            u0 = u0.detach().requires_grad_(True)
+
+            def drop(x, k):
+                if keep_prob == 1.0:
+                    return x
+                mk = masks[k] if masks is not None else torch.floor(torch.rand_like(x) + keep_prob)
+                return x / keep_prob * mk
+            h0 = drop(act(u0), 0)                                             # :88
+            h1 = drop(act(h0 @ self.dense['w1'] + self.dense['b1']), 1)       # :90-91
+            u = drop(act(h1 @ self.dense['w2'] + self.dense['b2']), 2)        # :93-94
+            return u.detach().contiguous(), ('mlp', lookup, u0, u)
+        u, _ = m.get_batch_user(keep_prob, False, dropout_mask=masks[0] if masks else None)   # :78
+        mask = getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None
+        return u, ('linear', m._last_user, keep_prob, mask)
+
+    def _user_backward(self, ctx, dU):
+        m = self.att_emb
+        if ctx[0] == 'mlp':
+            _, lookup, u0, u = ctx
+            for w in self.dense.values():
+                w.grad = None
+            u.backward(dU)
+            du0 = u0.grad
+        else:
+            _, lookup, keep_prob, mask = ctx
+            if keep_prob != 1.0:
+                du0 = torch.empty_like(dU)
+                call('arx_scale_mask', dU.data_ptr(), mask.data_ptr(), 1.0 / keep_prob, dU.numel(),
+                     du0.data_ptr())
+            else:
+                du0 = dU
+        if lookup is not None:
+            prefix, rng, ids, mode = lookup
+            m.push_grad(prefix, rng, ids, mode, du0.contiguous())
+
+    # ------------------------------------------------------------------ step ----------
+    def step(self, session, user_input, item_input, neg_item_input=None, item_sampled=None,
+             item_sampled_id2idx=None, forward_only=False, recommend=False, recommend_new=False,
+             loss=None, run_op=None, run_meta=None, masks=None, sync=True):
+        """hmf_model.py:162-228.  `session`, `run_op`, `run_meta` are accepted and ignored.
+        masks: optional injected dropout masks (parity runs).  Returns a Python float loss
+        (train / eval), [batch_loss, batch_rank] for warp_eval, or int[mb, top_N] (recommend)."""
+        m = self.att_emb
+        keep_prob = 1.0 if (forward_only or recommend) else self.dropout       # :167-170
+        m.add_input({}, user_input, item_input, neg_item_input=neg_item_input, item_sampled=item_sampled,
+                    item_sampled_id2idx=item_sampled_id2idx, forward_only=forward_only,
+                    recommend=recommend, loss=loss)
+        mb = m.u_indices['input'].numel()
+        if recommend:
+            if recommend_new:
+                raise AttributeError("'LatentProductModel' object has no attribute 'indices_test'")  # :198
+            u, _ = self._user_tower(1.0, None)
+            logits = m.get_prediction(u)
+            idx = torch.empty((mb, self.top_N_items), dtype=torch.int32, device=self.device)
+            call('arx_topk_rows', logits.data_ptr(), mb, logits.shape[1], logits.stride(0), self.top_N_items,
+                 idx.data_ptr(), None)
+            return idx.cpu().numpy()                                           # :154,:200
+
+        item_ids = m._ids(item_input)
+        targets = m.item2logit_dev[item_ids.long()].contiguous()               # target_mapping :173
+        train = not forward_only
+        u, ctx = self._user_tower(keep_prob, masks)
+        eff = loss if loss is not None else self.loss_function
+        if eff == 'mw' and forward_only:
+            eff = 'warp'                                                       # loss_eval :130,:144
+        scale = self._scale(mb)
+
+        if eff == 'mw':
+            pre = m._out_prefix()
+            Ps, bs, sids = m.pool_catalog('sampled')                           # :112
+            S = Ps.shape[0]
+            logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
+            call('arx_gemm', u.data_ptr(), Ps.data_ptr(), logits.data_ptr(), mb, S, self.size, 0, 1,
+                 bs.data_ptr(), 1.0, 0.0)
+            tscore = m.get_target_score(u, item_ids)                           # :115
+            _, Pt, _ = m._last_target
+            batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+            if train:
+                D, dts = logits, m._last_dtarget
+                dU = torch.empty_like(u)
+                call('arx_gemm', D.data_ptr(), Ps.data_ptr(), dU.data_ptr(), mb, self.size, S, 0, 0, None, 1.0, 0.0)
+                dPs = torch.empty_like(Ps)
+                call('arx_gemm', D.data_ptr(), u.data_ptr(), dPs.data_ptr(), S, self.size, mb, 1, 0, None, 1.0, 0.0)
+                dbs = D.sum(0)
+                dPt = torch.empty_like(Pt)
+                call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
+                     dU.data_ptr(), dPt.data_ptr())
+                rng = m.sets[pre].attr_range()
+                m.push_grad(pre, rng, sids, POOL_MEAN, dPs, dbs)
+                m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)
+        else:
+            logits = m.get_prediction(u)                                       # :118
+            _, P, beta, cids, _, _ = m._last_pred
+            out = m.compute_loss(logits, targets, eff, loss_func=self.loss_func, exp_p=self.loss_exp_p,
+                                 row_scale=scale, want_grad=train, forward_only=forward_only)
+            if eff == 'warp_eval':
+                return [out[0].cpu().numpy(), out[1].cpu().numpy()]            # :203-204,:220-221
+            batch_loss = out
+            if train:
+                D = logits
+                V = D.shape[1]
+                dU = torch.empty_like(u)
+                call('arx_gemm', D.data_ptr(), P.data_ptr(), dU.data_ptr(), mb, self.size, V, 0, 0, None, 1.0, 0.0)
+                dP = torch.empty_like(P)
+                call('arx_gemm', D.data_ptr(), u.data_ptr(), dP.data_ptr(), V, self.size, mb, 1, 0, None, 1.0, 0.0)
+                dbeta = D.sum(0)
+                pre = m._out_prefix()
+                m.push_grad(pre, m.sets[pre].attr_range(), cids, POOL_MEAN, dP, dbeta, plan_key='catalog')
+
+        loss_val = batch_loss.mean()                                           # :140
+        if train:
+            self._user_backward(ctx, dU)
+            lr = self.learning_rate.eval()
+            m.apply_gradients(lr, OPT_ADAGRAD)                                 # :146-151
+            for name, w in self.dense.items():
+                if w.grad is not None:
+                    call('arx_dense_update', w.data.data_ptr(), self.dense_acc[name].data_ptr(),
+                         w.grad.contiguous().data_ptr(), w.numel(), float(lr), None, OPT_ADAGRAD)
+            self.global_step.assign(self.global_step.eval() + 1)
+        self.batch_loss = batch_loss
+        return float(loss_val.item()) if sync else loss_val
+
+    # ------------------------------------------------------------------ batching ------
+    def get_batch(self, data, loss='ce', hist=None):
+        """hmf_model.py:230-241: mb independent random.choice draws (with replacement)."""
+        batch_user_input, batch_item_input = [], []
+        for _ in range(self.batch_size):
+            u, i, _t = random.choice(data)
+            batch_user_input.append(u)
+            batch_item_input.append(i)
+        return batch_user_input, batch_item_input, []
+
+    def get_permuted_batch(self, data):
+        """hmf_model.py:243-260."""
+        if self.data_length is None:
+            self.data_length = len(data)
+            self.start_index = 0
+            self.train_permutation = np.random.permutation(self.data_length)
+        if self.start_index + self.batch_size >= self.data_length:
+            self.start_index = 0
+            self.train_permutation = np.random.permutation(self.data_length)
+        indices = self.train_permutation[self.start_index:self.start_index + self.batch_size]
+        self.start_index += self.batch_size
+        batch_user_input = [data[j][0] for j in indices]
+        batch_item_input = [data[j][1] for j in indices]
+        return batch_user_input, batch_item_input, None

@@ -1,0 +1,198 @@
+/* arx_b200.h — C ABI of the B200-native A-RecSys hot path (libarx_b200.so).
+ *
+ * The reference (skywaLKer518/A-Recsys) is pure Python over TensorFlow-1 ops; it has
+ * no FFI of its own.  Each entry point below replaces the TF-op call sites of one
+ * row of SURVEY.md section 8(a) (file:line relative to the reference root).  The
+ * reference-side binding a maintainer would add is the ctypes stub shown in
+ * INTEGRATION.md; the in-repo host side is a-recsys_b200/_lib.py.
+ *
+ * Conventions: all pointers are DEVICE pointers unless the name says host; indices
+ * are int32, data fp32 row-major; every call enqueues on `stream` (a cudaStream_t
+ * passed as void*) and returns immediately; return value 0 = ok, <0 = ARX_E_*;
+ * no global state, caller owns all buffers; nothing throws.
+ */
+#ifndef ARX_B200_H_
+#define ARX_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARX_OK              0
+#define ARX_E_BADARG       -1
+#define ARX_E_LAUNCH       -2   /* cudaGetLastError() != cudaSuccess after a launch */
+#define ARX_E_UNSUPPORTED  -3
+#define ARX_E_CAPACITY     -4
+
+#define ARX_ABI_VERSION     1
+#define ARX_MAX_ATTRS      64
+
+/* One attribute (= one embedding table) of one entity side.  Mirrors the per-attribute
+ * arrays of attributes/attribute.py:7-47 as uploaded by embed_attribute.py:308-318,
+ * plus the variables of embed_attribute.py:265-306. */
+typedef struct arx_attr_desc {
+  float*         table;      /* E_f  [vocab, dim]                                   */
+  float*         table_acc;  /* Adagrad accumulator [vocab, dim] or NULL            */
+  float*         bias;       /* beta_f [vocab] or NULL (user side has none)         */
+  float*         bias_acc;   /* [vocab] or NULL                                     */
+  const int32_t* values;     /* kind 0: features_cat[f]   [N+1]
+                                kind 1: features_mulhot[f] flat token ids [nnz+1]   */
+  const int32_t* starts;     /* kind 1: mulhot_starts[f]  [N+2]; kind 0: NULL       */
+  const int32_t* lengths;    /* kind 1: mulhot_lengths[f] [N+1]; kind 0: NULL       */
+  int32_t*       touch;      /* [vocab] zero-initialised scratch owned by the table;
+                                left all-zero again by arx_pool_bwd_plan            */
+  int64_t        vocab;
+  int32_t        kind;       /* 0 = categorical, 1 = multi-hot                      */
+  int32_t        reserved;
+} arx_attr_desc;
+
+#define ARX_POOL_MEAN    0   /* out[n, dim]      = (1/F) sum_f pooled_f   (reduce_mean over attrs,
+                                embed_attribute.py:219,:235)                                        */
+#define ARX_POOL_CONCAT  1   /* out[n, f*dim ..] = pooled_f               (concat, embed_attribute.py:415;
+                                also the per-attribute list when read with a stride)               */
+
+/* K1+K2 — replaces EmbeddingAttribute._get_embedded (attributes/embed_attribute.py:350-417)
+ * and the batch_slice2/batch_segids2 index builders (attributes/mulhot_index.py:48-67):
+ * gather + segment mean of every attribute of `n` entities, fused mean/concat over
+ * attributes and pooled bias.  attrs: device array of n_attr descriptors. */
+int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim,
+                 const int32_t* ent_ids, int64_t n,
+                 float* out, int64_t out_stride, int mode,
+                 float* bias_out /* [n] or NULL */, void* stream);
+
+/* Integer part of K2 only (mulhot_index.py:48-67): flat token index and segment id
+ * vectors for one multi-hot attribute; bit-exact parity target.  offsets[n+1] is an
+ * exclusive scan of the bag lengths computed by the caller (device). */
+int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const int32_t* ent_ids,
+                          int64_t n, const int64_t* offsets, int32_t* flat_idx,
+                          int32_t* seg_ids, void* stream);
+
+/* Backward plan: the de-duplicated (table,row) list of a batch of entities and, per
+ * row, the bucket of (source position, weight) pairs that contribute to it.  Depends
+ * only on ent_ids, so it is cached for the catalog and for the sampled pool. */
+typedef struct arx_bwd_plan {
+  int32_t* counters;   /* [8]: 0 n_unique, 1 cursor, 2 overflow, 3 n_occ               */
+  int32_t* uniq_tok;   /* [cap_rows] token id                                          */
+  int32_t* uniq_attr;  /* [cap_rows] index into attrs                                  */
+  int32_t* row_base;   /* [cap_rows] first bucket slot                                 */
+  int32_t* row_cnt;    /* [cap_rows] bucket size                                       */
+  int32_t* bucket_src; /* [cap_occ]  row of the gradient arena that contributes         */
+  float*   bucket_w;   /* [cap_occ]  1/(F*len) (mean) or 1/len (concat)                */
+  int64_t  cap_rows;
+  int64_t  cap_occ;
+} arx_bwd_plan;
+
+/* K2b part 1 — replaces the IndexedSlices bookkeeping of tf.gradients through
+ * embedding_lookup/unsorted_segment_sum (hmf/hmf_model.py:149) and the duplicate-index
+ * summation of the sparse optimizer apply.  Phased so that several lookups of the same
+ * tables in one step (target items + sampled pool; the T input steps of the LSTM) are
+ * de-duplicated together:  begin, count*, alloc, fill*, end.  Each count/fill pair
+ * names a contiguous attribute range [attr_begin, attr_begin+n_attr) of `attrs`
+ * (no_id = skip attribute 0, no_attribute = attribute 0 only; embed_attribute.py:356-373)
+ * and the first row (row_base) its gradients occupy in the row arena handed to
+ * arx_pool_bwd_apply: MEAN mode -> row_base + i, weight 1/(n_attr*len);
+ * CONCAT mode -> row_base + i*n_attr + f, weight 1/len. */
+int arx_bwd_plan_begin(arx_bwd_plan plan, void* stream);
+int arx_bwd_plan_count(const arx_attr_desc* attrs, int attr_begin, int n_attr,
+                       const int32_t* ent_ids, int64_t n, arx_bwd_plan plan, void* stream);
+int arx_bwd_plan_alloc(const arx_attr_desc* attrs, arx_bwd_plan plan, void* stream);
+int arx_bwd_plan_fill(const arx_attr_desc* attrs, int attr_begin, int n_attr,
+                      const int32_t* ent_ids, int64_t n, int mode, int64_t row_base,
+                      arx_bwd_plan plan, void* stream);
+int arx_bwd_plan_end(const arx_attr_desc* attrs, arx_bwd_plan plan, void* stream);
+/* one-shot form for a single lookup over all n_attr attributes (row_base 0) */
+int arx_pool_bwd_plan(const arx_attr_desc* attrs, int n_attr, const int32_t* ent_ids,
+                      int64_t n, int mode, arx_bwd_plan plan, void* stream);
+
+#define ARX_OPT_ADAGRAD 0   /* tf.train.AdagradOptimizer: acc += g^2; w -= lr*g/sqrt(acc) (acc0 = 0.1) */
+#define ARX_OPT_SGD     1   /* tf.train.GradientDescentOptimizer (lstm/seqModel.py:176)              */
+#define ARX_OPT_NONE    2   /* write summed row gradients to rows_out instead (oracle check)         */
+
+/* K2b part 2 — segment-reduce the row arena dout [R, dout_stride] (first dim columns of
+ * each row) over every bucket and apply the optimizer to the touched rows only
+ * (hmf/hmf_model.py:146-151).  dbias: [R] aligned with the arena rows, or NULL;
+ * grad_scale_dev (device scalar or NULL) multiplies the summed gradient
+ * (clip_by_global_norm, lstm/seqModel.py:180); rows_out/bias_rows_out
+ * ([n_unique, dim] / [n_unique]) only for ARX_OPT_NONE. */
+int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int dim,
+                       arx_bwd_plan plan, const float* dout, int64_t dout_stride,
+                       const float* dbias, float lr, const float* grad_scale_dev,
+                       int opt, float* rows_out, float* bias_rows_out, void* stream);
+
+/* sum over occurrences of ||w * dOut[row]||^2 (+ bias part) — the IndexedSlices term of
+ * tf.clip_by_global_norm (lstm/seqModel.py:180); accumulates into *sumsq (device). */
+int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_plan plan, const float* dout,
+                       int64_t dout_stride, const float* dbias, float* sumsq, void* stream);
+
+/* K3/K4 dense contraction  C[m,n] = alpha * A[m,k] * op(B) + bias  (fp32 in/out).
+ * trans_b = 1: B is [n,k] (scores = U * P^T, embed_attribute.py:171,188 after the
+ * pool-first rewrite);  trans_b = 0: B is [k,n];  trans_a = 1: A is [k,m] (dP = D^T U).
+ * bias_n [n] (or NULL) is added along columns. */
+int arx_gemm(const float* A, const float* B, float* C, int64_t m, int64_t n, int64_t k,
+             int trans_a, int trans_b, const float* bias_n, float alpha, float beta,
+             void* stream);
+
+/* loss kinds: embed_attribute.py:525-649 */
+#define ARX_LOSS_CE       0
+#define ARX_LOSS_WARP     1   /* = rs + log                                   */
+#define ARX_LOSS_RS       2
+#define ARX_LOSS_RS_SIG   3
+#define ARX_LOSS_RS_SIG2  4
+#define ARX_LOSS_BBPR     5
+#define ARX_LOSS_MW       6   /* sampled; target score supplied separately     */
+/* loss_func transforms: embed_attribute.py:580-592 */
+#define ARX_LF_LOG 0
+#define ARX_LF_EXP 1
+#define ARX_LF_POLY 2
+#define ARX_LF_POLY2 3
+#define ARX_LF_LINEAR 4
+#define ARX_LF_SQUARE 5
+
+/* K5/K6 — per-row loss over materialised scores [mb, V] and, in place, the gradient
+ * d(mean loss)/d scores (scaled by row_scale[b], e.g. 1/mb or w_bt/(sum_t w)).
+ * target: [mb] column index (CE/WARP/RS*) ; target_score: [mb] (MW) ;
+ * positives as CSR (pos_ptr[R+1], pos_idx[L]) of masked columns — replaces the dense
+ * bool mask variable of embed_attribute.py:651-672,721-747.  pos_row[mb] (or NULL =
+ * identity) selects the CSR row of batch row b (e.g. the user index into a per-user
+ * CSR built once by prepare_warp); negative pos_idx entries are ignored; rows must be
+ * sorted ascending when V > 32768.
+ * Outputs: loss[mb]; dscores (may alias scores, or NULL for forward only);
+ * dtarget[mb] (MW only, or NULL); rank_out[mb] (true rank, warp_eval :635-637, or NULL). */
+int arx_loss_rows(const float* scores, int64_t mb, int64_t V, int64_t ld,
+                  const int32_t* target, const float* target_score,
+                  const int32_t* pos_row, const int32_t* pos_ptr, const int32_t* pos_idx,
+                  int loss_kind, int loss_func, float exp_p, const float* row_scale,
+                  float* loss, float* dscores, float* dtarget, int64_t* rank_out,
+                  void* stream);
+
+/* K4 — target_score[b] = U[b].P[b] + beta[b] (embed_attribute.py:219-220) and its adjoint
+ * dU[b] += dts[b] P[b]; dP[b] = dts[b] U[b]. */
+int arx_rowdot_fwd(const float* U, const float* P, const float* beta, int64_t mb, int dim,
+                   float* out, void* stream);
+int arx_rowdot_bwd(const float* U, const float* P, const float* dts, int64_t mb, int dim,
+                   float* dU_accum, float* dP, void* stream);
+
+/* K10 — tf.nn.top_k(sorted=True) over materialised scores (hmf/hmf_model.py:154):
+ * descending, ties -> lower index. idx_out [mb,k] int32, val_out [mb,k] or NULL. */
+int arx_topk_rows(const float* scores, int64_t mb, int64_t V, int64_t ld, int k,
+                  int32_t* idx_out, float* val_out, void* stream);
+
+/* K11 — dense Adagrad / SGD on a flat parameter (hmf_model.py:146-151). */
+int arx_dense_update(float* w, float* acc, const float* g, int64_t n, float lr,
+                     const float* grad_scale_dev, int opt, void* stream);
+
+/* elementwise helpers used by the towers: dropout with an injected/generated mask
+ * (tf.nn.dropout, embed_attribute.py:236): y = x * mask / keep. */
+int arx_scale_mask(const float* x, const float* mask, float scale, int64_t n, float* y,
+                   void* stream);
+
+int arx_abi_version(void);
+const char* arx_build_info(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ARX_B200_H_ */

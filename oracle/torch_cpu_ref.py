@@ -1,0 +1,207 @@
+"""PyTorch-CPU restatement of the reference HMF training step.  TEST / BASELINE INFRASTRUCTURE
+ONLY (see oracle/np_oracle.py header; PARITY UNPINNED for the same reasons).
+
+Executes the reference's op sequence *literally* (index_select -> segment-sum (index_add_) ->
+div -> mean over attributes -> dropout -> token-score matmul -> index_select -> segment-sum ->
+div -> mean -> transpose -> loss -> autograd -> Adagrad), i.e. attributes/embed_attribute.py:
+148-220, :350-417, :525-649 and hmf/hmf_model.py:75-151, on the host cores.  Two uses:
+  * an independent (autograd) derivation of every gradient the NumPy oracle derives by hand;
+  * the timed CPU baseline of bench.py (`cpu_baseline`, `--impl reference`): it omits the TF-1
+    session / feed_dict overhead and the two extra mask session.runs, so it is faster than the
+    real reference and every reported speed-up is conservative.
+"""
+import numpy as np
+import torch
+
+
+def _t(a, dtype):
+    return torch.as_tensor(np.asarray(a), dtype=dtype)
+
+
+def _flat(att, i, inds):
+    """mulhot_index.py:48-67, vectorised."""
+    s = att.mulhot_starts[i][inds].astype(np.int64)
+    l = att.mulhot_lengths[i][inds].astype(np.int64)
+    seg = np.repeat(np.arange(len(inds), dtype=np.int64), l)
+    off = np.concatenate([[0], np.cumsum(l)[:-1]])
+    pos = np.arange(int(l.sum()), dtype=np.int64) - np.repeat(off, l) + np.repeat(s, l)
+    return torch.from_numpy(att.features_mulhot[i][pos].astype(np.int64)), torch.from_numpy(seg), l
+
+
+def seg_sum(data, seg, n):
+    out = torch.zeros((n,) + tuple(data.shape[1:]), dtype=data.dtype)
+    return out.index_add_(0, seg, data)
+
+
+class TorchRefHMF(object):
+    def __init__(self, user_attributes, item_attributes, params, logit_ind2item_ind, item_ind2logit_ind,
+                 loss='ce', nonlinear='linear', keep_prob=1.0, learning_rate=0.1, n_sampled=None,
+                 loss_func='log', loss_exp_p=1.005, dtype=torch.float32):
+        self.ua, self.ia = user_attributes, item_attributes
+        self.dtype = dtype
+        self.p = {k: _t(v, dtype).clone().requires_grad_(True) for k, v in params.items()}
+        self.acc = {k: torch.full_like(v, 0.1) for k, v in self.p.items()}
+        self.l2i, self.i2l = logit_ind2item_ind, item_ind2logit_ind
+        self.V = len(logit_ind2item_ind)
+        self.loss, self.nonlinear, self.keep_prob, self.lr = loss, nonlinear, keep_prob, learning_rate
+        self.n_sampled, self.loss_func, self.exp_p = n_sampled, loss_func, loss_exp_p
+        ia = item_attributes
+        self.full = ([torch.from_numpy(np.asarray(a, dtype=np.int64)) for a in ia.full_cat_tr],
+                     [torch.from_numpy(np.asarray(a, dtype=np.int64)) for a in ia.full_values_tr],
+                     [torch.from_numpy(np.asarray(a, dtype=np.int64)) for a in ia.full_segids_tr],
+                     [_t(a, dtype).reshape(-1, 1) for a in ia.full_lengths_tr])
+        self.sampled = None
+        self.pos, self.pos_eval = None, None
+
+    # embed_attribute.py:350-417
+    def get_embedded(self, prefix, att, inds, with_bias):
+        inds = np.asarray(inds, dtype=np.int64)
+        mb = len(inds)
+        outs, biases = [], []
+        for i in range(att.num_features_cat):
+            tok = torch.from_numpy(att.features_cat[i][inds].astype(np.int64))
+            outs.append(self.p['%sembed_cat_%d' % (prefix, i)].index_select(0, tok))
+            if with_bias:
+                biases.append(self.p['%s_bias_cat_%d' % (prefix, i)].index_select(0, tok))
+        for i in range(att.num_features_mulhot):
+            idx, seg, l = _flat(att, i, inds)
+            lengs = torch.from_numpy(l).to(self.dtype).reshape(mb, 1)
+            flat = self.p['%sembed_mulhot_%d' % (prefix, i)].index_select(0, idx)
+            outs.append(seg_sum(flat, seg, mb) / lengs)
+            if with_bias:
+                bflat = self.p['%s_bias_mulhot_%d' % (prefix, i)].index_select(0, idx)
+                biases.append(seg_sum(bflat, seg, mb) / lengs)
+        bias = torch.stack(biases, 0).mean(0).reshape(-1) if with_bias else None
+        return outs, bias
+
+    # embed_attribute.py:320-348
+    def pass_sampled_items(self, item_sampled):
+        ia = self.ia
+        inds = np.asarray(item_sampled, dtype=np.int64)
+        cat = [torch.from_numpy(ia.features_cat[i][inds].astype(np.int64)) for i in range(ia.num_features_cat)]
+        val, seg, leng = [], [], []
+        for i in range(ia.num_features_mulhot):
+            a, b, l = _flat(ia, i, inds)
+            val.append(a); seg.append(b)
+            leng.append(torch.from_numpy(l).to(self.dtype).reshape(-1, 1))
+        self.sampled = (cat, val, seg, leng)
+        self.sampled_id2idx = {int(v): k for k, v in enumerate(inds)}
+
+    # embed_attribute.py:148-206 (output_feat = 1)
+    def get_prediction(self, u, pool='full'):
+        ia = self.ia
+        cat, val, seg, leng = self.full if pool == 'full' else self.sampled
+        V = self.V if pool == 'full' else self.n_sampled
+        innerps = []
+        for i in range(ia.num_features_cat):
+            innerp = self.p['itemembed_cat_%d' % i] @ u.t() + self.p['item_bias_cat_%d' % i]
+            innerps.append(innerp.index_select(0, cat[i]))
+        for i in range(ia.num_features_mulhot):
+            innerp = self.p['itemembed_mulhot_%d' % i] @ u.t() + self.p['item_bias_mulhot_%d' % i]
+            innerps.append(seg_sum(innerp.index_select(0, val[i]), seg[i], V) / leng[i])
+        return torch.stack(innerps, 0).mean(0).t()
+
+    # embed_attribute.py:208-220
+    def get_target_score(self, u, inds):
+        outs, bias = self.get_embedded('item', self.ia, inds, True)
+        return (u * torch.stack(outs, 0).mean(0)).sum(1) + bias
+
+    def build_mask(self, user_input, loss, forward_only):
+        V = self.n_sampled if loss == 'mw' else self.V
+        mask = np.ones((len(user_input), V), dtype=bool)
+        item_set = self.pos_eval if forward_only else self.pos
+        for c, uu in enumerate(user_input):
+            if uu in item_set:
+                for v in item_set[uu]:
+                    if loss == 'mw':
+                        if v in self.sampled_id2idx:
+                            mask[c, self.sampled_id2idx[v]] = False
+                    else:
+                        mask[c, self.i2l[v]] = False
+        return torch.from_numpy(mask)
+
+    # embed_attribute.py:525-649
+    def compute_loss(self, logits, target, loss, mask):
+        mb = logits.shape[0]
+        if loss == 'ce':
+            return torch.nn.functional.cross_entropy(logits, target, reduction='none')
+        zero = torch.zeros_like(logits)
+        if loss == 'mw':
+            t = torch.where(mask, logits - target.reshape(mb, 1) + 1, zero)
+            return torch.log(1 + torch.relu(t).sum(1))
+        tl = logits.gather(1, target.reshape(mb, 1))
+        if loss == 'warp':
+            t = torch.where(mask, logits - tl + 1, zero)
+            return torch.log(1 + torch.relu(t).sum(1))
+        if loss in ('rs', 'rs-sig'):
+            err = torch.relu(logits - tl + 1)
+        else:
+            err = torch.sigmoid(logits - tl)
+        em = torch.where(mask, err, zero)
+        if loss == 'rs-sig':
+            em = torch.sigmoid(em) * 2 - 1
+        s = em.sum(1)
+        if loss == 'bbpr':
+            return s
+        f, p = self.loss_func, self.exp_p
+        if f == 'log':
+            return torch.log(1 + s)
+        if f == 'exp':
+            return 1 - torch.pow(torch.tensor(p, dtype=self.dtype), -s)
+        if f == 'poly':
+            return torch.pow(s, p)
+        if f == 'poly2':
+            return torch.pow(1 + s, p)
+        if f == 'linear':
+            return s
+        return s * s
+
+    def _drop(self, x, keep, mask):
+        if keep == 1.0:
+            return x
+        if mask is None:
+            mask = torch.floor(torch.rand_like(x) + keep)
+        return x / keep * _t(mask, self.dtype)
+
+    def forward(self, user_input, item_input, forward_only=False, masks=None):
+        keep = 1.0 if forward_only else self.keep_prob
+        outs, _ = self.get_embedded('user', self.ua, user_input, False)
+        u = torch.stack(outs, 0).mean(0)
+        mk = (lambda k: masks[k] if masks is not None else None)
+        if self.nonlinear in ('relu', 'tanh'):
+            act = torch.relu if self.nonlinear == 'relu' else torch.tanh
+            h0 = self._drop(act(u), keep, mk(0))
+            h1 = self._drop(act(h0 @ self.p['w1'] + self.p['b1']), keep, mk(1))
+            u = self._drop(act(h1 @ self.p['w2'] + self.p['b2']), keep, mk(2))
+        else:
+            u = self._drop(u, keep, mk(0))
+        eff = 'warp' if (self.loss == 'mw' and forward_only) else self.loss
+        mask = self.build_mask(user_input, eff, forward_only) if eff != 'ce' else None
+        if eff == 'mw':
+            logits = self.get_prediction(u, 'sampled')
+            ts = self.get_target_score(u, item_input)
+            bl = self.compute_loss(logits, ts, 'mw', mask)
+        else:
+            logits = self.get_prediction(u)
+            tgt = torch.as_tensor([self.i2l[int(v)] for v in item_input], dtype=torch.int64)
+            bl = self.compute_loss(logits, tgt, eff, mask)
+        return bl.mean(), logits
+
+    def step(self, user_input, item_input, item_sampled=None, forward_only=False, masks=None):
+        if item_sampled is not None and self.loss == 'mw':
+            self.pass_sampled_items(item_sampled)
+        if forward_only:
+            with torch.no_grad():
+                return float(self.forward(user_input, item_input, True, masks)[0])
+        loss, _ = self.forward(user_input, item_input, False, masks)
+        names = list(self.p.keys())
+        grads = torch.autograd.grad(loss, [self.p[k] for k in names], allow_unused=True)
+        self.last_grads = {}
+        with torch.no_grad():
+            for k, g in zip(names, grads):
+                if g is None:
+                    continue
+                self.last_grads[k] = g
+                self.acc[k] += g * g
+                self.p[k] -= self.lr * g / torch.sqrt(self.acc[k])
+        return float(loss)

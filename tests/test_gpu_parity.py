@@ -1,0 +1,278 @@
+"""GPU parity tests: every C-ABI kernel and the HMF training step against the NumPy oracle on
+identical seeded inputs and injected weights / dropout masks.  Bars: bit-exact for index
+results; fp32 within the stated tolerance (north_star: 1e-3 relative on loss/logits; the
+exact-fp32 SIMT path is held to 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import small_dataset, random_params, positives, kat_item_attributes
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5      # fp32 kernels vs float64 oracle
+
+
+def _dicts(l2i):
+    l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+    i2l_d = {int(l2i[v]): int(v) for v in range(len(l2i))}
+    return i2l_d, l2i_d
+
+
+def _build(dim, mb=16, n_users=60, n_items=50, n_mulhot=3, vocab_m=25, max_len=7, seed=0, n_sampled=None,
+           loss='ce', nonlinear='linear', keep_prob=1.0, lr=0.3, logit_size=None, hidden=5, loss_func='log',
+           exp_p=1.005):
+    from arecsys_b200.hmf.hmf_model import LatentProductModel
+    ua, ia, i2l, l2i = small_dataset(n_users, n_items, n_mulhot, vocab_m, 3, max_len, seed, logit_size, dim)
+    params = random_params(ua, ia, dim, seed + 1, mlp_hidden=hidden if nonlinear != 'linear' else None)
+    i2l_d, l2i_d = _dicts(l2i)
+    model = LatentProductModel(n_users, n_items, dim, 1, mb, lr, 1.0, ua, ia, i2l_d, l2i_d, loss_function=loss,
+                               nonlinear=nonlinear, dropout=keep_prob, n_sampled=n_sampled, hidden_size=hidden,
+                               loss_func=loss_func, loss_exp_p=exp_p, params=params, top_N_items=10)
+    emb = O.OracleEmbeddingAttribute(ua, ia, mb, n_sampled, params, item_ind2logit_ind=i2l_d,
+                                     logit_ind2item_ind=l2i_d, dtype=np.float64)
+    omodel = O.OracleHMF(emb, loss=loss, nonlinear=nonlinear, keep_prob=keep_prob, learning_rate=lr,
+                         loss_func=loss_func, loss_exp_p=exp_p)
+    return model, omodel, ua, ia
+
+
+@pytest.mark.parametrize('dim', [4, 6, 8, 20, 32, 64, 128, 256])
+def test_pool_fwd_matches_oracle(cuda, dim):
+    model, om, ua, ia = _build(dim)
+    m, e = model.att_emb, om.emb
+    rng = np.random.default_rng(3)
+    ids = np.concatenate([rng.integers(0, 50, 37), [50]])            # includes the START pseudo-entity
+    from arecsys_b200._lib import POOL_MEAN, POOL_CONCAT
+    out, b, _ = m.pool('item', m._ids(ids), POOL_MEAN, True)
+    cat, mul = e._tables('item', ia); bc, bm = e._biases('item', ia)
+    P, bp = O.pool_entities(e, cat, mul, bc, bm, ia, ids)
+    np.testing.assert_allclose(out.cpu().numpy(), P, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(b.cpu().numpy(), bp, rtol=RTOL, atol=1e-6)
+    outc, _, _ = m.pool('item', m._ids(ids), POOL_CONCAT, True)
+    cc, bb = e._get_embedded(cat, mul, bc, bm, ids, ia, concatenation=True)
+    np.testing.assert_allclose(outc.cpu().numpy(), cc, rtol=RTOL, atol=1e-6)
+    # no_attribute keeps categorical attribute 0 only; no_id drops it (embed_attribute.py:356-373)
+    o2, _, _ = m.pool('item', m._ids(ids), POOL_MEAN, True, no_attribute=True)
+    c2, m2, _ = e._get_embedded(cat, mul, bc, bm, ids, ia, concatenation=False, no_attribute=True)
+    np.testing.assert_allclose(o2.cpu().numpy(), np.mean(np.stack(c2 + m2), 0), rtol=RTOL, atol=1e-6)
+    ucat, umul = e._tables('user', ua)
+    uids = rng.integers(0, 60, 20)
+    o3, _, _ = m.pool('user', m._ids(uids), POOL_CONCAT, False, no_id=True)
+    c3, _ = e._get_embedded(ucat, umul, None, None, uids, ua, concatenation=True, no_id=True)
+    np.testing.assert_allclose(o3.cpu().numpy(), c3, rtol=RTOL, atol=1e-6)
+
+
+def test_reference_facing_api_get_batch_user_item(cuda):
+    model, om, ua, ia = _build(8)
+    m, e = model.att_emb, om.emb
+    m.input_steps = 1
+    users = list(range(16)); items = [list(range(16, 32))]
+    m.add_input({}, users, items)
+    u, ub = m.get_batch_user(1.0, concat=False)
+    ou, _ = e.get_batch_user(users, 1.0, False)
+    np.testing.assert_allclose(u.cpu().numpy(), ou, rtol=RTOL, atol=1e-6)
+    lst, b = m.get_batch_item('input0', 16, concat=False)
+    olst, ob = e.get_batch_item(items[0], concat=False)
+    assert len(lst) == len(olst) == ia.num_features_cat + ia.num_features_mulhot
+    for a, c in zip(lst, olst):
+        np.testing.assert_allclose(a.cpu().numpy(), c, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(b.cpu().numpy(), ob, rtol=RTOL, atol=1e-6)
+    assert m.get_user_model_size(concat=True) == 8 * (ua.num_features_cat + ua.num_features_mulhot)
+    assert m.get_item_model_size(concat=False) == 8
+
+
+def test_flat_index_bit_exact_kat1_and_random(cuda):
+    model, om, ua, ia = _build(8)
+    m, e = model.att_emb, om.emb
+    rng = np.random.default_rng(5)
+    ids = rng.integers(0, 51, 64)
+    for f in range(ia.num_features_mulhot):
+        flat, seg = m.flat_indices('item', ia.num_features_cat + f, ids)
+        oi, os_ = e.flat_indices(ia, f, ids)
+        assert np.array_equal(flat.cpu().numpy().astype(np.int64), oi)
+        assert np.array_equal(seg.cpu().numpy().astype(np.int64), os_)
+    # KAT-1
+    from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
+    k = kat_item_attributes()
+    ke = EmbeddingAttribute(k, k, 4, None, logit_ind2item_ind={0: 0, 1: 1, 2: 2}, item_ind2logit_ind={0: 0, 1: 1, 2: 2},
+                            params={'userembed_mulhot_0': [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10]],
+                                    'itemembed_mulhot_0': [[1, 2], [3, 4], [5, 6], [7, 8], [9, 10]],
+                                    'item_bias_mulhot_0': [[.1], [.2], [.3], [.4], [.5]]})
+    flat, seg = ke.flat_indices('item', 0, [2, 0, 1, 3])
+    assert flat.cpu().tolist() == [3, 4, 4, 0, 2, 1, 1] and seg.cpu().tolist() == [0, 0, 0, 1, 1, 2, 3]
+    out, b, _ = ke.pool('item', ke._ids([2, 0, 1, 3]), 0, True)
+    np.testing.assert_allclose(out.cpu().numpy(), [[25 / 3, 28 / 3], [3, 4], [3, 4], [3, 4]], rtol=1e-6)
+    # KAT-2
+    U = torch.tensor([[1, 0], [.5, -1]], dtype=torch.float32, device='cuda')
+    logits = ke.get_prediction(U)
+    np.testing.assert_allclose(logits.cpu().numpy(), [[3.2, 3.2, 8.8], [-2.3, -2.3, -4.7]], rtol=1e-6)
+    ce = ke.compute_loss(logits, [2, 0], 'ce', want_grad=False)
+    np.testing.assert_allclose(ce.cpu().numpy(), [0.0073685, 0.7375075], atol=2e-6)
+
+
+@pytest.mark.parametrize('dim,mode', [(8, 0), (8, 1), (20, 0), (6, 0), (128, 0), (128, 1)])
+def test_pool_bwd_row_gradients_match_oracle(cuda, dim, mode):
+    model, om, ua, ia = _build(dim)
+    m, e = model.att_emb, om.emb
+    rng = np.random.default_rng(7)
+    ids1 = rng.integers(0, 51, 40); ids2 = rng.integers(0, 51, 24)    # two lookups, duplicates across both
+    F = ia.num_features_cat + ia.num_features_mulhot
+    w = dim * (F if mode == 1 else 1)
+    d1 = rng.standard_normal((40, w)).astype(np.float32); d2 = rng.standard_normal((24, w)).astype(np.float32)
+    b1 = rng.standard_normal(40).astype(np.float32); b2 = rng.standard_normal(24).astype(np.float32)
+    rngA = m.sets['item'].attr_range()
+    m.push_grad('item', rngA, m._ids(ids1), mode, torch.tensor(d1, device='cuda'), torch.tensor(b1, device='cuda'))
+    m.push_grad('item', rngA, m._ids(ids2), mode, torch.tensor(d2, device='cuda'), torch.tensor(b2, device='cuda'))
+    got = m.row_gradients('item')
+    cat, mul = e._tables('item', ia)
+    sc, sm = [t.shape for t in cat], [t.shape for t in mul]
+    tot = None
+    for ids, d, b in ((ids1, d1, b1), (ids2, d2, b2)):
+        if mode == 0:
+            g = O.pool_backward(ia, ids, d.astype(np.float64), b.astype(np.float64), sc, sm)
+        else:   # concat: attribute f reads its own column block and is not divided by F
+            g = None
+            for f in range(F):
+                blk = np.zeros((len(ids), dim)); blk[:] = d[:, f * dim:(f + 1) * dim]
+                gi = O.pool_backward(ia, ids, blk * F, b.astype(np.float64), sc, sm)   # bias stays a mean
+                keep = lambda lst, k, off: [a if (i + off) == k else np.zeros_like(a) for i, a in enumerate(lst)]
+                gi = (keep(gi[0], f, 0), keep(gi[1], f, len(sc)), keep(gi[2], f, 0), keep(gi[3], f, len(sc)))
+                g = gi if g is None else tuple([a + c for a, c in zip(x, y)] for x, y in zip(g, gi))
+        tot = g if tot is None else tuple([a + c for a, c in zip(x, y)] for x, y in zip(tot, g))
+    gc, gm, gbc, gbm = tot
+    for i in range(ia.num_features_cat):
+        np.testing.assert_allclose(got['itemembed_cat_%d' % i].cpu().numpy(), gc[i], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(got['item_bias_cat_%d' % i].cpu().numpy(), gbc[i], rtol=1e-4, atol=1e-5)
+    for i in range(ia.num_features_mulhot):
+        np.testing.assert_allclose(got['itemembed_mulhot_%d' % i].cpu().numpy(), gm[i], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(got['item_bias_mulhot_%d' % i].cpu().numpy(), gbm[i], rtol=1e-4, atol=1e-5)
+    for t in m.touch.values():                     # the plan leaves the scratch arrays clean
+        assert int(t.abs().sum().item()) == 0
+
+
+@pytest.mark.parametrize('shape', [(5, 7, 3), (64, 64, 16), (130, 77, 33), (16, 300, 128)])
+def test_gemm_variants(cuda, shape):
+    from arecsys_b200._lib import call
+    M, N, K = shape
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((M, K)).astype(np.float32); B = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    dA, dB, db = (torch.tensor(x, device='cuda') for x in (A, B, bias))
+    C = torch.empty((M, N), device='cuda')
+    call('arx_gemm', dA.data_ptr(), dB.data_ptr(), C.data_ptr(), M, N, K, 0, 1, db.data_ptr(), 1.0, 0.0)
+    np.testing.assert_allclose(C.cpu().numpy(), A.astype(np.float64) @ B.T.astype(np.float64) + bias, rtol=1e-4, atol=1e-4)
+    Bn = torch.tensor(np.ascontiguousarray(B.T), device='cuda')          # [K, N]
+    call('arx_gemm', dA.data_ptr(), Bn.data_ptr(), C.data_ptr(), M, N, K, 0, 0, None, 2.0, 0.0)
+    np.testing.assert_allclose(C.cpu().numpy(), 2 * (A.astype(np.float64) @ B.T), rtol=1e-4, atol=1e-4)
+    At = torch.tensor(np.ascontiguousarray(A.T), device='cuda')          # [K, M]
+    call('arx_gemm', At.data_ptr(), Bn.data_ptr(), C.data_ptr(), M, N, K, 1, 0, None, 1.0, 0.0)
+    np.testing.assert_allclose(C.cpu().numpy(), A.astype(np.float64) @ B.T, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize('loss', ['ce', 'warp', 'rs', 'rs-sig', 'rs-sig2', 'bbpr', 'mw'])
+@pytest.mark.parametrize('V', [9, 300, 40000])
+def test_loss_rows_match_oracle(cuda, loss, V):
+    from arecsys_b200 import _lib
+    rng = np.random.default_rng(13)
+    mb = 6
+    x = rng.standard_normal((mb, V)).astype(np.float32) * 2
+    tgt = rng.integers(0, V, mb).astype(np.int32)
+    ts = rng.standard_normal(mb).astype(np.float32)
+    n_rows = 10
+    pos = [np.unique(rng.integers(0, V, rng.integers(0, 6))) for _ in range(n_rows)]
+    prow = rng.integers(0, n_rows, mb).astype(np.int32)
+    if loss != 'mw':
+        for b in range(mb):                                  # training mask contains the target itself
+            pos[prow[b]] = np.unique(np.append(pos[prow[b]], tgt[b]))
+    pptr = np.concatenate([[0], np.cumsum([len(p) for p in pos])]).astype(np.int32)
+    pidx = np.concatenate(pos + [np.zeros(0, dtype=np.int64)]).astype(np.int32)
+    mask = np.ones((mb, V), dtype=bool)
+    for b in range(mb):
+        mask[b, pos[prow[b]]] = False
+    scale = rng.uniform(0.1, 1.0, mb).astype(np.float32)
+    l, d, dts = O.loss_and_grad(x.astype(np.float64), ts.astype(np.float64) if loss == 'mw' else tgt.astype(np.int64),
+                                loss, mask, 'log', 1.005)
+    dx = torch.tensor(x, device='cuda'); out = torch.empty(mb, device='cuda'); dd = torch.empty_like(dx)
+    dt = torch.empty(mb, device='cuda'); rank = torch.empty(mb, dtype=torch.int64, device='cuda')
+    T = lambda a: torch.tensor(a, device='cuda')
+    _lib.call('arx_loss_rows', dx.data_ptr(), mb, V, V, T(tgt).data_ptr(), T(ts).data_ptr(), T(prow).data_ptr(),
+              T(pptr).data_ptr(), T(pidx).data_ptr() if len(pidx) else None, _lib.LOSS_KIND[loss], 0, 1.005,
+              T(scale).data_ptr(), out.data_ptr(), dd.data_ptr(), dt.data_ptr(), rank.data_ptr())
+    np.testing.assert_allclose(out.cpu().numpy(), l, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(dd.cpu().numpy(), d * scale[:, None], rtol=1e-3, atol=2e-6)
+    if loss == 'mw':
+        np.testing.assert_allclose(dt.cpu().numpy(), dts * scale, rtol=1e-3, atol=1e-5)
+    if loss == 'warp':
+        xt = x[np.arange(mb), tgt][:, None]
+        assert np.array_equal(rank.cpu().numpy(), ((x > xt) & mask).sum(1))
+
+
+@pytest.mark.parametrize('loss,nonlinear,dim', [('ce', 'linear', 8), ('ce', 'linear', 32), ('warp', 'linear', 8),
+                                                ('rs', 'linear', 8), ('bbpr', 'linear', 20), ('mw', 'linear', 8),
+                                                ('mw', 'linear', 128), ('ce', 'relu', 8), ('warp', 'tanh', 8),
+                                                ('mw', 'tanh', 8), ('ce', 'linear', 128)])
+def test_hmf_training_steps_match_oracle(cuda, loss, nonlinear, dim):
+    ns = 12 if loss == 'mw' else None
+    mb = 16
+    model, om, ua, ia = _build(dim, mb=mb, n_sampled=ns, loss=loss, nonlinear=nonlinear, keep_prob=0.5)
+    rng = np.random.default_rng(17)
+    for it in range(4):
+        users = rng.integers(0, 60, mb); items = rng.integers(0, 50, mb)
+        if it == 3:
+            users[:4] = users[4]; items[:3] = items[5]           # duplicates inside the batch
+        pos = positives(users, items, 60, rng, n_items=50)
+        model.prepare_warp(pos, pos); om.emb.prepare_warp(pos, pos)
+        sampled = [int(v) for v in rng.permutation(50)[:ns]] if (ns and it % 2 == 0) else None
+        id2idx = {v: k for k, v in enumerate(sampled)} if sampled else None
+        shapes = [(mb, dim), (mb, 5), (mb, dim)] if nonlinear != 'linear' else [(mb, dim)]
+        masks = [np.floor(rng.random(s) + 0.5) for s in shapes]
+        tm = [torch.tensor(k, dtype=torch.float32, device='cuda') for k in masks]
+        l_gpu = model.step(None, list(users), list(items), None, sampled, id2idx, loss=loss, masks=tm)
+        l_ora = om.step(list(users), list(items), sampled, id2idx, masks=masks)
+        assert abs(l_gpu - l_ora) <= 1e-4 * max(1.0, abs(l_ora)), (it, l_gpu, l_ora)
+        for k, v in om.emb.p.items():
+            got = (model.att_emb.params[k] if k in model.att_emb.params else model.dense[k].data).cpu().numpy()
+            np.testing.assert_allclose(got.reshape(v.shape), v, rtol=1e-3, atol=2e-5, err_msg='%s step %d' % (k, it))
+    users = rng.integers(0, 60, mb); items = rng.integers(0, 50, mb)
+    pos = positives(users, items, 60, rng, n_items=50)
+    model.prepare_warp(pos, pos); om.emb.prepare_warp(pos, pos)
+    e_gpu = model.step(None, list(users), list(items), forward_only=True, loss=loss)
+    e_ora = om.step(list(users), list(items), forward_only=True)
+    assert abs(e_gpu - e_ora) <= 1e-4 * max(1.0, abs(e_ora))
+    assert model.global_step.eval() == 4
+
+
+def test_topk_and_recommend_match_oracle(cuda):
+    model, om, ua, ia = _build(8, mb=16, loss='ce')
+    users = list(range(16))
+    rec = model.step(None, users, None, forward_only=True, recommend=True)
+    idx, _ = om.top_k(users, 10)
+    assert rec.shape == (16, 10) and np.array_equal(rec, idx)
+    # ties -> lower index first; large V exercises the radix select
+    from arecsys_b200._lib import call
+    x = torch.zeros((3, 5000), device='cuda'); x[1, 4000] = 1.0; x[2, ::7] = 2.0
+    out = torch.empty((3, 100), dtype=torch.int32, device='cuda'); val = torch.empty((3, 100), device='cuda')
+    call('arx_topk_rows', x.data_ptr(), 3, 5000, 5000, 100, out.data_ptr(), val.data_ptr())
+    o = out.cpu().numpy()
+    assert o[0].tolist() == list(range(100))
+    assert o[1].tolist() == [4000] + list(range(99))
+    assert o[2].tolist() == list(range(0, 700, 7))
+    xr = torch.randn((4, 30011), device='cuda')
+    out = torch.empty((4, 64), dtype=torch.int32, device='cuda')
+    call('arx_topk_rows', xr.data_ptr(), 4, 30011, 30011, 64, out.data_ptr(), None)
+    ref = torch.topk(xr, 64, dim=1).indices.cpu().numpy()
+    assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def test_checkpoint_roundtrip(cuda, tmp_path):
+    model, om, ua, ia = _build(8, loss='ce', keep_prob=1.0)
+    users = list(range(16)); items = list(range(16))
+    model.step(None, users, items, loss='ce')
+    p = model.saver.save(None, str(tmp_path / 'best.ckpt'), global_step=0)
+    before = {k: v.clone() for k, v in model.att_emb.params.items()}
+    model.step(None, users, items, loss='ce')
+    model.saver.restore(None, p)
+    for k, v in before.items():
+        assert torch.equal(model.att_emb.params[k], v)
+    assert model.global_step.eval() == 1

@@ -59,8 +59,12 @@ def test_pool_fwd_matches_oracle(cuda, dim):
     ucat, umul = e._tables('user', ua)
     uids = rng.integers(0, 60, 20)
     o3, _, _ = m.pool('user', m._ids(uids), POOL_CONCAT, False, no_id=True)
-    c3, _ = e._get_embedded(ucat, umul, None, None, uids, ua, concatenation=True, no_id=True)
-    np.testing.assert_allclose(o3.cpu().numpy(), c3, rtol=RTOL, atol=1e-6)
+    c3, _ = e._get_embedded(ucat, umul, None, None, uids, ua, concatenation=True, no_id=False)
+    np.testing.assert_allclose(o3.cpu().numpy(), c3[:, dim:], rtol=RTOL, atol=1e-6)   # attribute 0 dropped
+    # reference quirk (:356-366): no_id with a single categorical attribute returns zeros [mb, dim]
+    z, _ = m.get_batch_user(1.0, concat=True, no_id=True, u_inds=uids)
+    z0, _ = e._get_embedded(ucat, umul, None, None, uids, ua, concatenation=True, no_id=True)
+    assert z.shape == z0.shape and float(z.abs().sum()) == 0.0 and not z0.any()
 
 
 def test_reference_facing_api_get_batch_user_item(cuda):
@@ -195,10 +199,13 @@ def test_loss_rows_match_oracle(cuda, loss, V):
                                 loss, mask, 'log', 1.005)
     dx = torch.tensor(x, device='cuda'); out = torch.empty(mb, device='cuda'); dd = torch.empty_like(dx)
     dt = torch.empty(mb, device='cuda'); rank = torch.empty(mb, dtype=torch.int64, device='cuda')
-    T = lambda a: torch.tensor(a, device='cuda')
-    _lib.call('arx_loss_rows', dx.data_ptr(), mb, V, V, T(tgt).data_ptr(), T(ts).data_ptr(), T(prow).data_ptr(),
-              T(pptr).data_ptr(), T(pidx).data_ptr() if len(pidx) else None, _lib.LOSS_KIND[loss], 0, 1.005,
-              T(scale).data_ptr(), out.data_ptr(), dd.data_ptr(), dt.data_ptr(), rank.data_ptr())
+    # keep every device buffer alive until the kernel has run (the caching allocator would
+    # hand a freed temporary to the next torch.tensor() before the launch)
+    g_tgt, g_ts, g_prow, g_pptr, g_scale = (torch.tensor(a, device='cuda') for a in (tgt, ts, prow, pptr, scale))
+    g_pidx = torch.tensor(pidx if len(pidx) else np.zeros(1, dtype=np.int32), device='cuda')
+    _lib.call('arx_loss_rows', dx.data_ptr(), mb, V, V, g_tgt.data_ptr(), g_ts.data_ptr(), g_prow.data_ptr(),
+              g_pptr.data_ptr(), g_pidx.data_ptr(), _lib.LOSS_KIND[loss], 0, 1.005,
+              g_scale.data_ptr(), out.data_ptr(), dd.data_ptr(), dt.data_ptr(), rank.data_ptr())
     np.testing.assert_allclose(out.cpu().numpy(), l, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(dd.cpu().numpy(), d * scale[:, None], rtol=1e-3, atol=2e-6)
     if loss == 'mw':

@@ -26,8 +26,9 @@ class AttrDesc(ctypes.Structure):
 class BwdPlan(ctypes.Structure):
     """arx_bwd_plan (include/arx_b200.h)."""
     _fields_ = [('counters', vp), ('uniq_tok', vp), ('uniq_attr', vp), ('row_base', vp),
-                ('row_cnt', vp), ('bucket_src', vp), ('bucket_w', vp),
-                ('cap_rows', ctypes.c_int64), ('cap_occ', ctypes.c_int64)]
+                ('row_cnt', vp), ('bucket_src', vp), ('bucket_w', vp), ('chunk_row', vp),
+                ('row_chunk0', vp), ('row_done', vp), ('partials', vp),
+                ('cap_rows', ctypes.c_int64), ('cap_occ', ctypes.c_int64), ('cap_chunks', ctypes.c_int64)]
 
 
 POOL_MEAN, POOL_CONCAT = 0, 1
@@ -96,11 +97,23 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+timeline = None    # when a list: (name, tag, start_event, end_event) per call (bench.py roofline leg)
+tag = ''           # free-form label the host sets to tell apart uses of one kernel (e.g. 'user'/'item')
+
+
 def call(name, *args):
     """Invoke a C-ABI entry point on torch's current stream; raise on any error code."""
     global launch_count
     lib = load()
-    rc = getattr(lib, name)(*args, stream())
+    if timeline is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*args, stream())
+        e1.record()
+        timeline.append((name, tag, e0, e1))
+    else:
+        rc = getattr(lib, name)(*args, stream())
     launch_count += 1
     if rc != 0:
         raise RuntimeError('%s failed: %s (%d)' % (name, _ERR.get(rc, '?'), rc))

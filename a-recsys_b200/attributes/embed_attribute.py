@@ -85,8 +85,13 @@ class _TableSet(object):
 class _Plan(object):
     """Device buffers of one arx_bwd_plan."""
 
-    def __init__(self, device, cap_rows, cap_occ):
+    def __init__(self, device, cap_rows, cap_occ, dim):
         i32 = dict(dtype=torch.int32, device=device)
+        cap_chunks = cap_occ // 32 + 1
+        self.chunk_row = torch.empty(cap_chunks, **i32)
+        self.row_chunk0 = torch.empty(cap_rows, **i32)
+        self.row_done = torch.zeros(cap_rows, **i32)
+        self.partials = torch.empty(cap_chunks * (dim + 1), dtype=torch.float32, device=device)
         self.counters = torch.zeros(8, **i32)
         self.uniq_tok = torch.empty(cap_rows, **i32)
         self.uniq_attr = torch.empty(cap_rows, **i32)
@@ -97,7 +102,8 @@ class _Plan(object):
         self.cap_rows, self.cap_occ = cap_rows, cap_occ
         self.c = BwdPlan(self.counters.data_ptr(), self.uniq_tok.data_ptr(), self.uniq_attr.data_ptr(),
                          self.row_base.data_ptr(), self.row_cnt.data_ptr(), self.bucket_src.data_ptr(),
-                         self.bucket_w.data_ptr(), cap_rows, cap_occ)
+                         self.bucket_w.data_ptr(), self.chunk_row.data_ptr(), self.row_chunk0.data_ptr(),
+                         self.row_done.data_ptr(), self.partials.data_ptr(), cap_rows, cap_occ, cap_chunks)
 
 
 class EmbeddingAttribute(object):
@@ -217,6 +223,7 @@ class EmbeddingAttribute(object):
             out = torch.empty((n, width), dtype=torch.float32, device=self.device)
         if want_bias and bias_out is None:
             bias_out = torch.empty((n,), dtype=torch.float32, device=self.device)
+        _lib.tag = prefix
         call('arx_pool_fwd', ts.desc_ptr(a0), na, self.dim, ids.data_ptr(), n, out.data_ptr(),
              out.stride(0), mode, ptr(bias_out) if want_bias else None)
         return out, (bias_out if want_bias else None), (a0, na)
@@ -492,7 +499,8 @@ class EmbeddingAttribute(object):
             cap_occ = int(ids.numel()) * ts.n_cat + sum(len(v) for v in ia.full_values_tr)
         cap_occ = max(cap_occ, 1)
         cap_rows = max(min(cap_occ, ts.total_vocab), 1)
-        plan = _Plan(self.device, cap_rows, cap_occ) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
+        plan = _Plan(self.device, cap_rows, cap_occ, self.dim) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
+        _lib.tag = ts.prefix
         call('arx_bwd_plan_begin', plan.c)
         for (a0, na, ids, mode, dout, dbias, key) in entries:
             call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
@@ -509,7 +517,7 @@ class EmbeddingAttribute(object):
     def _scratch_plan(self, ts, cap_rows, cap_occ):
         p = getattr(ts, '_scratch', None)
         if p is None or p.cap_rows < cap_rows or p.cap_occ < cap_occ:
-            p = _Plan(self.device, cap_rows, cap_occ)
+            p = _Plan(self.device, cap_rows, cap_occ, self.dim)
             ts._scratch = p
         return p
 
@@ -557,6 +565,7 @@ class EmbeddingAttribute(object):
             else:
                 plan = self._plan_for(ts, ts.pending)
                 arena, bias = self._arena(ts.pending)
+            _lib.tag = ts.prefix
             call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
                  arena.stride(0), ptr(bias), float(lr), ptr(grad_scale), opt, None, None)
             ts.pending = []

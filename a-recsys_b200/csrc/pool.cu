@@ -12,6 +12,7 @@ namespace {
 
 constexpr int kMaxAttr = 32;          // one lane per attribute for the (start,len) prefetch
 constexpr int kRowsInFlight = 8;      // independent row loads per lane group
+constexpr int kHeavy = 64;            // bucket size above which a row is split across warps
 
 // ---- tiny vector abstraction: VEC = 4 (float4, dim % 4 == 0) or 1 (any dim) --------
 template <int VEC> struct V;
@@ -20,6 +21,7 @@ template <> struct V<4> {
   static __device__ __forceinline__ T zero() { return f4_zero(); }
   static __device__ __forceinline__ T ldg(const float* p) { return ldg_f4(p); }
   static __device__ __forceinline__ T ld(const float* p) { return ld_f4(p); }
+  static __device__ __forceinline__ T ldcg(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
   static __device__ __forceinline__ void st(float* p, T v) { st_f4(p, v); }
   static __device__ __forceinline__ void add(T& a, T b) { f4_add(a, b); }
   static __device__ __forceinline__ void fma(T& a, float w, T b) { f4_fma(a, w, b); }
@@ -47,6 +49,7 @@ template <> struct V<1> {
   static __device__ __forceinline__ T zero() { return 0.f; }
   static __device__ __forceinline__ T ldg(const float* p) { return __ldg(p); }
   static __device__ __forceinline__ T ld(const float* p) { return *p; }
+  static __device__ __forceinline__ T ldcg(const float* p) { return __ldcg(p); }
   static __device__ __forceinline__ void st(float* p, T v) { *p = v; }
   static __device__ __forceinline__ void add(T& a, T b) { a += b; }
   static __device__ __forceinline__ void fma(T& a, float w, T b) { a = fmaf(w, b, a); }
@@ -156,6 +159,95 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
   }
 }
 
+// ---- v2 forward: one warp per (entity, attribute) pair -------------------------------
+// A CTA owns EPB consecutive entities; its 8 warps stride over the EPB*n_attr bags, each
+// bag is gathered with >= 8 rows in flight, divided by its length and parked in shared
+// memory; after a barrier the attribute mean (fixed order => deterministic) is written
+// with 128-bit stores.  9x more warps than one-warp-per-entity: the 1024-entity sampled
+// pool still fills all 148 SMs, and no warp walks nine dependent bags in sequence.
+template <int GW, int VEC>
+__global__ void __launch_bounds__(256)
+pool_fwd2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
+                 const int* __restrict__ ids, long long n, float* __restrict__ out,
+                 long long out_stride, int mode, float* __restrict__ bias_out, int epb) {
+  using VT = typename V<VEC>::T;
+  extern __shared__ __align__(16) float s_pool[];        // [epb][n_attr][dim] then [epb][n_attr] bias
+  __shared__ arx_attr_desc s_attrs[kMaxAttr];
+  stage_descs(s_attrs, g_attrs, n_attr);
+  constexpr int NG = 32 / GW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int g = lane / GW, l = lane % GW;
+  const int nvec = dim / VEC;
+  float* s_bias = s_pool + (size_t)epb * n_attr * dim;
+  const float Ff = (float)n_attr;
+
+  for (long long e0 = (long long)blockIdx.x * epb; e0 < n; e0 += (long long)gridDim.x * epb) {
+    const int ne = (int)min((long long)epb, n - e0);
+    const int npairs = ne * n_attr;
+    for (int p = warp; p < npairs; p += nw) {
+      const int el = p / n_attr, f = p - el * n_attr;
+      const int e = __ldg(ids + e0 + el);
+      int s = e, L = 1;
+      if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
+      const float* __restrict__ table = s_attrs[f].table;
+      const int* __restrict__ values = s_attrs[f].values;
+      const float* __restrict__ bias = s_attrs[f].bias;
+      const bool want_bias = (bias_out != nullptr) && (bias != nullptr);
+      const float Lf = (float)L;
+      float bsum = 0.f;
+      for (int c0 = 0; c0 < nvec; c0 += GW) {
+        const int col = c0 + l;
+        const bool colok = col < nvec;
+        VT acc = V<VEC>::zero();
+        for (int j0 = 0; j0 < L; j0 += 32) {
+          const int cnt = min(32, L - j0);
+          const int tok = (lane < cnt) ? __ldg(values + s + j0 + lane) : 0;
+          if (want_bias && c0 == 0 && lane < cnt) bsum += __ldg(bias + tok);
+          for (int jj0 = 0; jj0 < cnt; jj0 += NG * kRowsInFlight) {
+            VT v[kRowsInFlight];
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) {
+              const int jj = jj0 + u * NG + g;
+              const int t = __shfl_sync(ARX_FULL_MASK, tok, jj & 31);
+              v[u] = (jj < cnt && colok) ? V<VEC>::ldg(table + (size_t)t * dim + (size_t)col * VEC)
+                                         : V<VEC>::zero();
+            }
+#pragma unroll
+            for (int u = 0; u < kRowsInFlight; ++u) V<VEC>::add(acc, v[u]);
+          }
+        }
+#pragma unroll
+        for (int o = GW; o < 32; o <<= 1) V<VEC>::add(acc, V<VEC>::shfl_xor(acc, o));
+        acc = V<VEC>::div(acc, Lf);                                  // tf.div(embedded_sum, lengs) :400
+        if (g == 0 && colok) {
+          if (mode == ARX_POOL_MEAN) V<VEC>::st(s_pool + ((size_t)el * n_attr + f) * dim + (size_t)col * VEC, acc);
+          else V<VEC>::st(out + (e0 + el) * out_stride + (size_t)f * dim + (size_t)col * VEC, acc);
+        }
+      }
+      if (bias_out != nullptr) {
+        const float b = want_bias ? warp_sum(bsum) / Lf : 0.f;       // :404-406
+        if (lane == 0) s_bias[el * n_attr + f] = b;
+      }
+    }
+    __syncthreads();
+    if (mode == ARX_POOL_MEAN) {
+      for (int i = threadIdx.x; i < ne * nvec; i += blockDim.x) {
+        const int el = i / nvec, col = i - el * nvec;
+        VT tot = V<VEC>::zero();
+        for (int f = 0; f < n_attr; ++f)
+          V<VEC>::add(tot, V<VEC>::ld(s_pool + ((size_t)el * n_attr + f) * dim + (size_t)col * VEC));
+        V<VEC>::st(out + (e0 + el) * out_stride + (size_t)col * VEC, V<VEC>::div(tot, Ff));   // reduce_mean :219,:235
+      }
+    }
+    if (bias_out != nullptr && threadIdx.x < ne) {
+      float b = 0.f;
+      for (int f = 0; f < n_attr; ++f) b += s_bias[threadIdx.x * n_attr + f];
+      bias_out[e0 + threadIdx.x] = b / Ff;                           // :412
+    }
+    __syncthreads();
+  }
+}
+
 // integer part of K2 (mulhot_index.py:48-67)
 __global__ void flat_index_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr,
                                   const int* __restrict__ ids, long long n,
@@ -187,24 +279,32 @@ plan_count_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long ei = warp0; ei < n; ei += nwarps) {
+  // one warp per (entity, attribute) bag; first-touch rows claim their slot in the unique
+  // list with ONE counter atomic per warp iteration (ballot + popc), not one per row.
+  const long long npairs = n * n_attr;
+  for (long long p = warp0; p < npairs; p += nwarps) {
+    const long long ei = p / n_attr;
+    const int f = (int)(p - ei * n_attr);
     const int e = __ldg(ids + ei);
-    int my_s, my_L;
-    fetch_bags(s_attrs, n_attr, lane, e, my_s, my_L);
-    int occ = my_L;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) occ += __shfl_xor_sync(ARX_FULL_MASK, occ, o);
-    if (lane == 0) atomicAdd(&plan.counters[3], occ);
-    for (int f = 0; f < n_attr; ++f) {
-      const int s = __shfl_sync(ARX_FULL_MASK, my_s, f);
-      const int L = __shfl_sync(ARX_FULL_MASK, my_L, f);
-      const int* __restrict__ values = s_attrs[f].values;
-      int* touch = s_attrs[f].touch;
-      for (int j = lane; j < L; j += 32) {
-        const int tok = __ldg(values + s + j);
-        const int c = atomicAdd(&touch[tok], 1);
-        if (c == 0) {
-          const int u = atomicAdd(&plan.counters[0], 1);
+    int s = e, L = 1;
+    if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
+    const int* __restrict__ values = s_attrs[f].values;
+    int* touch = s_attrs[f].touch;
+    for (int j0 = 0; j0 < L; j0 += 32) {
+      const int j = j0 + lane;
+      int tok = 0;
+      bool first = false;
+      if (j < L) {
+        tok = __ldg(values + s + j);
+        first = (atomicAdd(&touch[tok], 1) == 0);
+      }
+      const unsigned m = __ballot_sync(ARX_FULL_MASK, first);
+      if (m != 0u) {
+        int ub = 0;
+        if (lane == 0) ub = atomicAdd(&plan.counters[0], __popc(m));
+        ub = __shfl_sync(ARX_FULL_MASK, ub, 0);
+        if (first) {
+          const int u = ub + __popc(m & ((1u << lane) - 1u));
           if (u < plan.cap_rows) { plan.uniq_tok[u] = tok; plan.uniq_attr[u] = attr_begin + f; }
           else plan.counters[2] = 1;
         }
@@ -215,15 +315,40 @@ plan_count_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int
 
 __global__ void plan_alloc_kernel(const arx_attr_desc* __restrict__ g_attrs, arx_bwd_plan plan) {
   const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
-  for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x) {
-    const int tok = plan.uniq_tok[u];
-    int* touch = g_attrs[plan.uniq_attr[u]].touch;
-    const int c = touch[tok];
-    const int base = atomicAdd(&plan.counters[1], c);
+  const int lane = threadIdx.x & 31;
+  for (int u0 = blockIdx.x * blockDim.x + threadIdx.x - lane; u0 < nu; u0 += gridDim.x * blockDim.x) {
+    const int u = u0 + lane;
+    int tok = 0, c = 0;
+    int* touch = nullptr;
+    if (u < nu) {
+      tok = plan.uniq_tok[u];
+      touch = g_attrs[plan.uniq_attr[u]].touch;
+      c = touch[tok];
+    }
+    int incl = c;                                   // warp scan: one cursor atomic per 32 rows
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(ARX_FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int wb = 0;
+    if (lane == 31) wb = atomicAdd(&plan.counters[1], incl);
+    wb = __shfl_sync(ARX_FULL_MASK, wb, 31);
+    if (u >= nu) continue;
+    const int base = wb + incl - c;
     plan.row_base[u] = base;
     plan.row_cnt[u] = c;
     touch[tok] = base;                       // becomes the fill cursor of this row
     if ((long long)base + c > plan.cap_occ) plan.counters[2] = 1;
+    // hot rows (Zipf heads: thousands of contributions) are split into kHeavy-sized chunks
+    // that different warps reduce; the last chunk to arrive folds the partials and updates.
+    if (c > kHeavy) {
+      const int nch = (c + kHeavy - 1) / kHeavy;
+      const int cb = atomicAdd(&plan.counters[4], nch);
+      plan.row_chunk0[u] = cb;
+      if ((long long)cb + nch > plan.cap_chunks) { plan.counters[2] = 1; }
+      else for (int k = 0; k < nch; ++k) plan.chunk_row[cb + k] = u;
+    }
   }
 }
 
@@ -238,23 +363,22 @@ plan_fill_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int 
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   const float invF = (mode == ARX_POOL_MEAN) ? 1.0f / (float)n_attr : 1.0f;
-  for (long long ei = warp0; ei < n; ei += nwarps) {
+  const long long npairs = n * n_attr;
+  for (long long p = warp0; p < npairs; p += nwarps) {
+    const long long ei = p / n_attr;
+    const int f = (int)(p - ei * n_attr);
     const int e = __ldg(ids + ei);
-    int my_s, my_L;
-    fetch_bags(s_attrs, n_attr, lane, e, my_s, my_L);
-    for (int f = 0; f < n_attr; ++f) {
-      const int s = __shfl_sync(ARX_FULL_MASK, my_s, f);
-      const int L = __shfl_sync(ARX_FULL_MASK, my_L, f);
-      const int* __restrict__ values = s_attrs[f].values;
-      int* touch = s_attrs[f].touch;
-      const float w = invF / (float)L;
-      const int row = (mode == ARX_POOL_MEAN) ? (int)(row_base + ei) : (int)(row_base + ei * n_attr + f);
-      for (int j = lane; j < L; j += 32) {
-        const int tok = __ldg(values + s + j);
-        const int pos = atomicAdd(&touch[tok], 1);
-        plan.bucket_src[pos] = row;
-        plan.bucket_w[pos] = w;
-      }
+    int s = e, L = 1;
+    if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
+    const int* __restrict__ values = s_attrs[f].values;
+    int* touch = s_attrs[f].touch;
+    const float w = invF / (float)L;
+    const int row = (mode == ARX_POOL_MEAN) ? (int)(row_base + ei) : (int)(row_base + ei * n_attr + f);
+    for (int j = lane; j < L; j += 32) {
+      const int tok = __ldg(values + s + j);
+      const int pos = atomicAdd(&touch[tok], 1);
+      plan.bucket_src[pos] = row;
+      plan.bucket_w[pos] = w;
     }
   }
 }
@@ -355,6 +479,229 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
   }
 }
 
+// ---- v2 of the apply kernel ---------------------------------------------------------
+// (a) hot rows are reduced chunk-by-chunk by many warps (last arriver folds + updates);
+// (b) the remaining rows are taken 32 at a time: one coalesced metadata load and one
+//     first-bucket-entry load per lane, then four rows per step with their table row,
+//     accumulator row and gradient row all in flight together (12 x 512 B per warp).
+template <int VEC>
+__device__ __forceinline__ typename V<VEC>::T
+reduce_bucket(const arx_bwd_plan& plan, int base, int cnt, const float* __restrict__ dout,
+              long long stride, int col, bool colok, int lane) {
+  using VT = typename V<VEC>::T;
+  VT g = V<VEC>::zero();
+  for (int k0 = 0; k0 < cnt; k0 += 32) {
+    const int kc = min(32, cnt - k0);
+    int src = 0; float w = 0.f;
+    if (lane < kc) { src = __ldg(plan.bucket_src + base + k0 + lane); w = __ldg(plan.bucket_w + base + k0 + lane); }
+    for (int kk0 = 0; kk0 < kc; kk0 += kRowsInFlight) {
+      VT v[kRowsInFlight]; float wk[kRowsInFlight];
+#pragma unroll
+      for (int q = 0; q < kRowsInFlight; ++q) {
+        const int kk = kk0 + q;
+        const int sk = __shfl_sync(ARX_FULL_MASK, src, kk & 31);
+        wk[q] = __shfl_sync(ARX_FULL_MASK, w, kk & 31);
+        v[q] = (kk < kc && colok) ? V<VEC>::ldg(dout + (size_t)sk * stride + (size_t)col * VEC) : V<VEC>::zero();
+      }
+#pragma unroll
+      for (int q = 0; q < kRowsInFlight; ++q) V<VEC>::fma(g, wk[q], v[q]);
+    }
+  }
+  return g;
+}
+
+// lane-parallel bias gradient of one bucket (every lane walks its own bucket)
+__device__ __forceinline__ float bucket_bias(const arx_bwd_plan& plan, int base, int cnt,
+                                             const float* __restrict__ dbias) {
+  float gb = 0.f;
+  for (int k = 0; k < cnt; ++k)
+    gb = fmaf(__ldg(plan.bucket_w + base + k), __ldg(dbias + __ldg(plan.bucket_src + base + k)), gb);
+  return gb;
+}
+
+__device__ __forceinline__ void bias_update(const arx_attr_desc& a, int tok, float gb, float lr, int opt) {
+  if (opt == ARX_OPT_ADAGRAD) {
+    const float acc = fmaf(gb, gb, a.bias_acc[tok]);
+    a.bias_acc[tok] = acc;
+    a.bias[tok] -= lr * gb / sqrtf(acc);
+  } else if (opt == ARX_OPT_SGD) {
+    a.bias[tok] -= lr * gb;
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void row_update(const arx_attr_desc& a, size_t off, typename V<VEC>::T g,
+                                           float lr, int opt) {
+  using VT = typename V<VEC>::T;
+  float* wp = a.table + off;
+  VT wv = V<VEC>::ld(wp);
+  if (opt == ARX_OPT_ADAGRAD) {
+    float* ap = a.table_acc + off;
+    VT av = V<VEC>::ld(ap);
+    V<VEC>::adagrad(wv, av, g, lr);
+    V<VEC>::st(ap, av);
+  } else {
+    V<VEC>::sgd(wv, g, lr);
+  }
+  V<VEC>::st(wp, wv);
+}
+
+constexpr int kRowsPerStep = 4;
+
+template <int VEC>
+__global__ void __launch_bounds__(256, 2)
+pool_bwd_apply2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
+                       arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
+                       const float* __restrict__ dbias, float lr,
+                       const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
+                       float* __restrict__ bias_rows_out) {
+  using VT = typename V<VEC>::T;
+  __shared__ arx_attr_desc s_attrs[kMaxAttr];
+  stage_descs(s_attrs, g_attrs, n_attr);
+  if (plan.counters[2] != 0) return;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = dim / VEC;
+  const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
+  const int nchunks = (int)min((long long)plan.counters[4], (long long)plan.cap_chunks);
+  const float gs = grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f;
+  float* __restrict__ part = plan.partials;
+  float* __restrict__ part_b = plan.partials + (size_t)plan.cap_chunks * dim;
+
+  // ---- phase 1: chunks of the hot rows (longest work first) ---------------------------
+  for (long long ch = warp0; ch < nchunks; ch += nwarps) {
+    const int u = plan.chunk_row[ch];
+    const int cb = plan.row_chunk0[u];
+    const int k = (int)ch - cb;
+    const int rc = plan.row_cnt[u];
+    const int base = plan.row_base[u] + k * kHeavy;
+    const int cnt = min(kHeavy, rc - k * kHeavy);
+    const int nch = (rc + kHeavy - 1) / kHeavy;
+    for (int c0 = 0; c0 < nvec; c0 += 32) {
+      const int col = c0 + lane;
+      const bool colok = col < nvec;
+      const VT g = reduce_bucket<VEC>(plan, base, cnt, dout, dout_stride, col, colok, lane);
+      if (colok) V<VEC>::st(part + (size_t)ch * dim + (size_t)col * VEC, g);
+    }
+    if (dbias != nullptr) {
+      float gb = 0.f;
+      for (int kk = lane; kk < cnt; kk += 32)
+        gb = fmaf(__ldg(plan.bucket_w + base + kk), __ldg(dbias + __ldg(plan.bucket_src + base + kk)), gb);
+      gb = warp_sum(gb);
+      if (lane == 0) part_b[ch] = gb;
+    }
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&plan.row_done[u], 1) == nch - 1) ? 1 : 0;
+    last = __shfl_sync(ARX_FULL_MASK, last, 0);
+    if (!last) continue;
+    __threadfence();
+    const int tok = plan.uniq_tok[u];
+    const int f = plan.uniq_attr[u];
+    for (int c0 = 0; c0 < nvec; c0 += 32) {
+      const int col = c0 + lane;
+      const bool colok = col < nvec;
+      VT g = V<VEC>::zero();
+      if (colok) {
+        for (int kk0 = 0; kk0 < nch; kk0 += kRowsInFlight) {      // fixed chunk order
+          VT v[kRowsInFlight];
+#pragma unroll
+          for (int q = 0; q < kRowsInFlight; ++q)
+            v[q] = (kk0 + q < nch) ? V<VEC>::ldcg(part + (size_t)(cb + kk0 + q) * dim + (size_t)col * VEC)
+                                   : V<VEC>::zero();
+#pragma unroll
+          for (int q = 0; q < kRowsInFlight; ++q) V<VEC>::add(g, v[q]);
+        }
+        g = V<VEC>::mul(g, gs);
+        if (opt == ARX_OPT_NONE) V<VEC>::st(rows_out + (size_t)u * dim + (size_t)col * VEC, g);
+        else row_update<VEC>(s_attrs[f], (size_t)tok * dim + (size_t)col * VEC, g, lr, opt);
+      }
+    }
+    if (lane == 0) {
+      float gb = 0.f;
+      if (dbias != nullptr && s_attrs[f].bias != nullptr) {
+        for (int kk = 0; kk < nch; ++kk) gb += __ldcg(part_b + cb + kk);
+        gb *= gs;
+        bias_update(s_attrs[f], tok, gb, lr, opt);
+      }
+      if (opt == ARX_OPT_NONE && bias_rows_out != nullptr) bias_rows_out[u] = gb;
+      plan.row_done[u] = 0;                                       // self-resetting for the next apply
+    }
+  }
+
+  // ---- phase 2: all other rows, 32 per warp iteration -----------------------------------
+  for (long long u0 = warp0 * 32; u0 < nu; u0 += nwarps * 32) {
+    const int u = (int)u0 + lane;
+    int tok = 0, f = 0, base = 0, cnt = 0;
+    if (u < nu) {
+      tok = __ldg(plan.uniq_tok + u); f = __ldg(plan.uniq_attr + u);
+      base = __ldg(plan.row_base + u); cnt = __ldg(plan.row_cnt + u);
+    }
+    const bool light = (u < nu) && (cnt <= kHeavy);
+    int src0 = 0; float w0 = 0.f;
+    if (light) { src0 = __ldg(plan.bucket_src + base); w0 = __ldg(plan.bucket_w + base); }
+    if (light) {                                 // bias column: each lane owns its row
+      float gb = 0.f;
+      if (dbias != nullptr && s_attrs[f].bias != nullptr) {
+        gb = bucket_bias(plan, base, cnt, dbias) * gs;
+        bias_update(s_attrs[f], tok, gb, lr, opt);
+      }
+      if (opt == ARX_OPT_NONE && bias_rows_out != nullptr) bias_rows_out[u] = gb;
+    }
+    const unsigned lightmask = __ballot_sync(ARX_FULL_MASK, light);
+    for (int c0 = 0; c0 < nvec; c0 += 32) {
+      const int col = c0 + lane;
+      const bool colok = col < nvec;
+      for (int r = 0; r < 32; r += kRowsPerStep) {
+        if (((lightmask >> r) & ((1u << kRowsPerStep) - 1u)) == 0u) continue;
+        VT Ev[kRowsPerStep], Av[kRowsPerStep], g[kRowsPerStep];
+        int tq[kRowsPerStep], fq[kRowsPerStep], cq[kRowsPerStep], bq[kRowsPerStep];
+#pragma unroll
+        for (int q = 0; q < kRowsPerStep; ++q) {
+          const int rr = r + q;
+          tq[q] = __shfl_sync(ARX_FULL_MASK, tok, rr);
+          fq[q] = __shfl_sync(ARX_FULL_MASK, f, rr);
+          cq[q] = ((lightmask >> rr) & 1u) ? __shfl_sync(ARX_FULL_MASK, cnt, rr) : 0;   // 0 = skip row
+          bq[q] = __shfl_sync(ARX_FULL_MASK, base, rr);
+          const int s0 = __shfl_sync(ARX_FULL_MASK, src0, rr);
+          const float wq = __shfl_sync(ARX_FULL_MASK, w0, rr);
+          const bool ok = (cq[q] > 0) && colok;
+          const size_t off = (size_t)tq[q] * dim + (size_t)col * VEC;
+          Ev[q] = V<VEC>::zero(); Av[q] = V<VEC>::zero();
+          if (ok && opt != ARX_OPT_NONE) {
+            Ev[q] = V<VEC>::ld(s_attrs[fq[q]].table + off);
+            if (opt == ARX_OPT_ADAGRAD) Av[q] = V<VEC>::ld(s_attrs[fq[q]].table_acc + off);
+          }
+          g[q] = ok ? V<VEC>::mul(V<VEC>::ldg(dout + (size_t)s0 * dout_stride + (size_t)col * VEC), wq)
+                    : V<VEC>::zero();
+        }
+#pragma unroll
+        for (int q = 0; q < kRowsPerStep; ++q) {
+          if (cq[q] > 1)                             // warp-uniform: remaining bucket entries
+            V<VEC>::add(g[q], reduce_bucket<VEC>(plan, bq[q] + 1, cq[q] - 1, dout, dout_stride, col, colok, lane));
+        }
+#pragma unroll
+        for (int q = 0; q < kRowsPerStep; ++q) {
+          if (cq[q] == 0 || !colok) continue;
+          const VT gq = V<VEC>::mul(g[q], gs);
+          const size_t off = (size_t)tq[q] * dim + (size_t)col * VEC;
+          if (opt == ARX_OPT_ADAGRAD) {
+            V<VEC>::adagrad(Ev[q], Av[q], gq, lr);
+            V<VEC>::st(s_attrs[fq[q]].table_acc + off, Av[q]);
+            V<VEC>::st(s_attrs[fq[q]].table + off, Ev[q]);
+          } else if (opt == ARX_OPT_SGD) {
+            V<VEC>::sgd(Ev[q], gq, lr);
+            V<VEC>::st(s_attrs[fq[q]].table + off, Ev[q]);
+          } else {
+            V<VEC>::st(rows_out + ((size_t)u0 + r + q) * dim + (size_t)col * VEC, gq);
+          }
+        }
+      }
+    }
+  }
+}
+
 // IndexedSlices part of the global norm: sum over occurrences of w^2 * ||dOut[src]||^2.
 __global__ void __launch_bounds__(256)
 pool_bwd_sumsq_kernel(int dim, arx_bwd_plan plan, const float* __restrict__ dout,
@@ -401,10 +748,19 @@ int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* i
                float* out, int64_t out_stride, int mode, float* bias_out, cudaStream_t st) {
   const int nvec = dim / VEC;
   const int threads = 256;
-  const int grid = pick_grid(n, threads);
-#define ARX_FWD(GW)                                                                             \
-  pool_fwd_kernel<GW, VEC><<<grid, threads, 0, st>>>(attrs, n_attr, dim, ids, (long long)n, out, \
-                                                     (long long)out_stride, mode, bias_out)
+  // entities per CTA: 4 when that still gives >= 2 CTAs per SM, fewer for small batches;
+  // bounded so the staging buffer stays under the 48 KB static-opt-in-free limit.
+  int epb = 4;
+  while (epb > 1 && (n + epb - 1) / epb < 2LL * arx_num_sms()) epb >>= 1;
+  while (epb > 1 && (size_t)epb * n_attr * (dim + 1) * sizeof(float) > 40 * 1024) epb >>= 1;
+  const size_t smem = (size_t)epb * n_attr * (dim + 1) * sizeof(float);
+  if (smem > 48 * 1024) return ARX_E_UNSUPPORTED;
+  long long blocks = (n + epb - 1) / epb;
+  const long long cap = (long long)arx_num_sms() * 32;
+  const int grid = (int)(blocks > cap ? cap : blocks);
+#define ARX_FWD(GW)                                                                                  \
+  pool_fwd2_kernel<GW, VEC><<<grid, threads, smem, st>>>(attrs, n_attr, dim, ids, (long long)n, out, \
+                                                         (long long)out_stride, mode, bias_out, epb)
   if (nvec >= 32) ARX_FWD(32);
   else if (nvec >= 16) ARX_FWD(16);
   else if (nvec >= 8) ARX_FWD(8);
@@ -443,7 +799,8 @@ extern "C" int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const
 
 static int plan_args_ok(const arx_bwd_plan& plan) {
   return plan.counters && plan.uniq_tok && plan.uniq_attr && plan.row_base && plan.row_cnt &&
-         plan.bucket_src && plan.bucket_w && plan.cap_rows >= 1 && plan.cap_occ >= 1;
+         plan.bucket_src && plan.bucket_w && plan.chunk_row && plan.row_chunk0 && plan.row_done &&
+         plan.partials && plan.cap_rows >= 1 && plan.cap_occ >= 1 && plan.cap_chunks >= 1;
 }
 
 extern "C" int arx_bwd_plan_begin(arx_bwd_plan plan, void* stream) {
@@ -458,7 +815,7 @@ extern "C" int arx_bwd_plan_count(const arx_attr_desc* attrs, int attr_begin, in
   if (!attrs || !ent_ids || attr_begin < 0 || n_attr < 1 || n_attr > kMaxAttr || n < 0 || !plan_args_ok(plan))
     return ARX_E_BADARG;
   if (n == 0) return ARX_OK;
-  plan_count_kernel<<<pick_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
+  plan_count_kernel<<<pick_grid(n * n_attr, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
                                                                         (long long)n, plan);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
@@ -478,7 +835,7 @@ extern "C" int arx_bwd_plan_fill(const arx_attr_desc* attrs, int attr_begin, int
     return ARX_E_BADARG;
   if (mode != ARX_POOL_MEAN && mode != ARX_POOL_CONCAT) return ARX_E_BADARG;
   if (n == 0) return ARX_OK;
-  plan_fill_kernel<<<pick_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
+  plan_fill_kernel<<<pick_grid(n * n_attr, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
                                                                        (long long)n, mode, (long long)row_base, plan);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
@@ -509,14 +866,14 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
   if (opt != ARX_OPT_ADAGRAD && opt != ARX_OPT_SGD && opt != ARX_OPT_NONE) return ARX_E_BADARG;
   if (opt == ARX_OPT_NONE && !rows_out) return ARX_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = arx_num_sms() * 8;   // persistent: warps stride over the device-side n_unique
+  const int grid = arx_num_sms() * 2;   // persistent (2 CTAs/SM): warps stride over the device-side row list
   const bool v4 = (dim % 4 == 0) && (dout_stride % 4 == 0) && (((uintptr_t)dout & 15) == 0);
   if (v4)
-    pool_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                   dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+    pool_bwd_apply2_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+                                                    dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
   else
-    pool_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                   dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+    pool_bwd_apply2_kernel<1><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+                                                    dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

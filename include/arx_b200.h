@@ -74,15 +74,20 @@ int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const int32_t* e
  * row, the bucket of (source position, weight) pairs that contribute to it.  Depends
  * only on ent_ids, so it is cached for the catalog and for the sampled pool. */
 typedef struct arx_bwd_plan {
-  int32_t* counters;   /* [8]: 0 n_unique, 1 cursor, 2 overflow, 3 n_occ               */
+  int32_t* counters;   /* [8]: 0 n_unique, 1 cursor, 2 overflow, 3 n_occ, 4 n_chunks   */
   int32_t* uniq_tok;   /* [cap_rows] token id                                          */
   int32_t* uniq_attr;  /* [cap_rows] index into attrs                                  */
   int32_t* row_base;   /* [cap_rows] first bucket slot                                 */
   int32_t* row_cnt;    /* [cap_rows] bucket size                                       */
   int32_t* bucket_src; /* [cap_occ]  row of the gradient arena that contributes         */
   float*   bucket_w;   /* [cap_occ]  1/(F*len) (mean) or 1/len (concat)                */
+  int32_t* chunk_row;  /* [cap_chunks] row of each 64-entry chunk of a hot row         */
+  int32_t* row_chunk0; /* [cap_rows]  first chunk of a hot row                         */
+  int32_t* row_done;   /* [cap_rows]  zero-initialised arrival counters (self-resetting)*/
+  float*   partials;   /* [cap_chunks*(dim+1)] chunk partial sums (+ bias partials)    */
   int64_t  cap_rows;
   int64_t  cap_occ;
+  int64_t  cap_chunks; /* >= cap_occ/32 + 1                                            */
 } arx_bwd_plan;
 
 /* K2b part 1 — replaces the IndexedSlices bookkeeping of tf.gradients through

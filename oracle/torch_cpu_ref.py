@@ -52,6 +52,7 @@ class TorchRefHMF(object):
                      [_t(a, dtype).reshape(-1, 1) for a in ia.full_lengths_tr])
         self.sampled = None
         self.pos, self.pos_eval = None, None
+        self.touched = {}
 
     # embed_attribute.py:350-417
     def get_embedded(self, prefix, att, inds, with_bias):
@@ -60,12 +61,14 @@ class TorchRefHMF(object):
         outs, biases = [], []
         for i in range(att.num_features_cat):
             tok = torch.from_numpy(att.features_cat[i][inds].astype(np.int64))
+            self.touched['%sembed_cat_%d' % (prefix, i)] = tok
             outs.append(self.p['%sembed_cat_%d' % (prefix, i)].index_select(0, tok))
             if with_bias:
                 biases.append(self.p['%s_bias_cat_%d' % (prefix, i)].index_select(0, tok))
         for i in range(att.num_features_mulhot):
             idx, seg, l = _flat(att, i, inds)
             lengs = torch.from_numpy(l).to(self.dtype).reshape(mb, 1)
+            self.touched['%sembed_mulhot_%d' % (prefix, i)] = idx
             flat = self.p['%sembed_mulhot_%d' % (prefix, i)].index_select(0, idx)
             outs.append(seg_sum(flat, seg, mb) / lengs)
             if with_bias:
@@ -202,6 +205,14 @@ class TorchRefHMF(object):
                 if g is None:
                     continue
                 self.last_grads[k] = g
+                if k.startswith('userembed') and k in self.touched:
+                    # tables reached only through lookups get IndexedSlices -> sparse apply in TF
+                    rows = torch.unique(self.touched[k])
+                    gr = g.index_select(0, rows)
+                    a = self.acc[k].index_select(0, rows) + gr * gr
+                    self.acc[k].index_copy_(0, rows, a)
+                    self.p[k].index_copy_(0, rows, self.p[k].index_select(0, rows) - self.lr * gr / torch.sqrt(a))
+                    continue
                 self.acc[k] += g * g
                 self.p[k] -= self.lr * g / torch.sqrt(self.acc[k])
         return float(loss)

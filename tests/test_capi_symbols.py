@@ -36,7 +36,7 @@ def test_abi_version_and_struct_layout():
     lib = _lib.load()
     assert lib.arx_abi_version() == 1
     assert ctypes.sizeof(_lib.AttrDesc) == 80      # 8 pointers + int64 + 2 x int32
-    assert ctypes.sizeof(_lib.BwdPlan) == 72       # 7 pointers + 2 x int64
+    assert ctypes.sizeof(_lib.BwdPlan) == 112      # 11 pointers + 3 x int64
     assert b'sm_100a' in lib.arx_build_info()
 
 

@@ -51,6 +51,9 @@ SIGNATURES = {
     'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
     'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, vp],
     'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
+    'arx_gemm_tc': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
+    'arx_transpose': [vp, i64, i64, vp, vp],
+    'arx_colsum': [vp, i64, i64, i64, vp, vp],
     'arx_loss_rows': [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
     'arx_rowdot_fwd': [vp, vp, vp, i64, i32, vp, vp],
     'arx_rowdot_bwd': [vp, vp, vp, i64, i32, vp, vp, vp],
@@ -115,6 +118,29 @@ def call(name, *args):
     else:
         rc = getattr(lib, name)(*args, stream())
     launch_count += 1
-    if rc != 0:
+    if rc != 0 and not (rc == -3 and name in _MAY_BE_UNSUPPORTED):
         raise RuntimeError('%s failed: %s (%d)' % (name, _ERR.get(rc, '?'), rc))
     return rc
+
+
+_MAY_BE_UNSUPPORTED = ('arx_gemm_tc',)
+exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
+
+
+def gemm(A, B, C, m, n, k, trans_a, trans_b, bias=None, alpha=1.0, beta=0.0):
+    """C = alpha * op(A) op(B) + bias: tensor cores (tcgen05, tf32) when TMA can describe the
+    operands, else the exact-fp32 SIMT kernel.  Both are this library's own CUDA kernels."""
+    if not exact_fp32 and k % 4 == 0 and k > 0:
+        # the tensor-core kernel takes K-major operands: A [m,k], B [n,k]; an operand stored the
+        # other way round is staged through arx_transpose first (small next to the contraction)
+        Ak, Bk = A, B
+        if trans_a:
+            Ak = torch.empty((m, k), dtype=torch.float32, device=A.device)
+            call('arx_transpose', A.data_ptr(), k, m, Ak.data_ptr())
+        if not trans_b:
+            Bk = torch.empty((n, k), dtype=torch.float32, device=B.device)
+            call('arx_transpose', B.data_ptr(), k, n, Bk.data_ptr())
+        if call('arx_gemm_tc', Ak.data_ptr(), Bk.data_ptr(), C.data_ptr(), m, n, k, 0, 1, ptr(bias),
+                alpha, beta) == 0:
+            return
+    call('arx_gemm', A.data_ptr(), B.data_ptr(), C.data_ptr(), m, n, k, trans_a, trans_b, ptr(bias), alpha, beta)

@@ -330,8 +330,7 @@ class EmbeddingAttribute(object):
         P, beta, ids = self.pool_catalog(pool, output_feat)
         mb, N = latent.shape[0], P.shape[0]
         logits = torch.empty((mb, N), dtype=torch.float32, device=self.device)
-        call('arx_gemm', latent.data_ptr(), P.data_ptr(), logits.data_ptr(), mb, N, self.dim, 0, 1,
-             beta.data_ptr(), 1.0, 0.0)
+        _lib.gemm(latent, P, logits, mb, N, self.dim, 0, 1, beta)
         self._last_pred = (latent, P, beta, ids, pool, output_feat)
         return logits
 

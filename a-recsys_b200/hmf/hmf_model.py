@@ -192,6 +192,18 @@ class LatentProductModel(object):
             prefix, rng, ids, mode = lookup
             m.push_grad(prefix, rng, ids, mode, du0.contiguous())
 
+    def _scores_backward(self, D, u, P):
+        """Adjoint of scores = u P^T + beta for D = d(loss)/d(scores) [mb, N]:
+        dU = D P, dP = D^T u, dbeta = column sums of D."""
+        mb, N = D.shape
+        dU = torch.empty_like(u)
+        _lib.gemm(D, P, dU, mb, self.size, N, 0, 0)
+        dP = torch.empty_like(P)
+        _lib.gemm(D, u, dP, N, self.size, mb, 1, 0)
+        dbeta = torch.empty((N,), dtype=torch.float32, device=self.device)
+        call('arx_colsum', D.data_ptr(), mb, N, D.stride(0), dbeta.data_ptr())
+        return dU, dP, dbeta
+
     # ------------------------------------------------------------------ step ----------
     def step(self, session, user_input, item_input, neg_item_input=None, item_sampled=None,
              item_sampled_id2idx=None, forward_only=False, recommend=False, recommend_new=False,
@@ -229,18 +241,13 @@ class LatentProductModel(object):
             Ps, bs, sids = m.pool_catalog('sampled')                           # :112
             S = Ps.shape[0]
             logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
-            call('arx_gemm', u.data_ptr(), Ps.data_ptr(), logits.data_ptr(), mb, S, self.size, 0, 1,
-                 bs.data_ptr(), 1.0, 0.0)
+            _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)
             tscore = m.get_target_score(u, item_ids)                           # :115
             _, Pt, _ = m._last_target
             batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
             if train:
                 D, dts = logits, m._last_dtarget
-                dU = torch.empty_like(u)
-                call('arx_gemm', D.data_ptr(), Ps.data_ptr(), dU.data_ptr(), mb, self.size, S, 0, 0, None, 1.0, 0.0)
-                dPs = torch.empty_like(Ps)
-                call('arx_gemm', D.data_ptr(), u.data_ptr(), dPs.data_ptr(), S, self.size, mb, 1, 0, None, 1.0, 0.0)
-                dbs = D.sum(0)
+                dU, dPs, dbs = self._scores_backward(D, u, Ps)
                 dPt = torch.empty_like(Pt)
                 call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
                      dU.data_ptr(), dPt.data_ptr())
@@ -257,12 +264,7 @@ class LatentProductModel(object):
             batch_loss = out
             if train:
                 D = logits
-                V = D.shape[1]
-                dU = torch.empty_like(u)
-                call('arx_gemm', D.data_ptr(), P.data_ptr(), dU.data_ptr(), mb, self.size, V, 0, 0, None, 1.0, 0.0)
-                dP = torch.empty_like(P)
-                call('arx_gemm', D.data_ptr(), u.data_ptr(), dP.data_ptr(), V, self.size, mb, 1, 0, None, 1.0, 0.0)
-                dbeta = D.sum(0)
+                dU, dP, dbeta = self._scores_backward(D, u, P)
                 pre = m._out_prefix()
                 m.push_grad(pre, m.sets[pre].attr_range(), cids, POOL_MEAN, dP, dbeta, plan_key='catalog')
 

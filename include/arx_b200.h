@@ -140,6 +140,21 @@ int arx_gemm(const float* A, const float* B, float* C, int64_t m, int64_t n, int
              int trans_a, int trans_b, const float* bias_n, float alpha, float beta,
              void* stream);
 
+/* Same contraction on the 5th-generation tensor cores: tcgen05.mma kind::tf32 (fp32 operands
+ * read as tf32, fp32 accumulation in TMEM), TMA-fed 4-stage pipeline, split-K when the output
+ * grid cannot fill 148 SMs.  Returns ARX_E_UNSUPPORTED when TMA cannot describe an operand
+ * (pitch or base not 16-byte aligned): the caller then uses arx_gemm. */
+int arx_gemm_tc(const float* A, const float* B, float* C, int64_t m, int64_t n, int64_t k,
+                int trans_a, int trans_b, const float* bias_n, float alpha, float beta,
+                void* stream);
+
+/* dst[c, r] = src[r, c] (fp32).  Stages an MN-major operand K-major for arx_gemm_tc. */
+int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream);
+
+/* out[c] = sum_r x[r, c] — the item-bias gradient: column sums of d(loss)/d(scores)
+ * (the `+ i_biases` terms of embed_attribute.py:171,188). */
+int arx_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream);
+
 /* loss kinds: embed_attribute.py:525-649 */
 #define ARX_LOSS_CE       0
 #define ARX_LOSS_WARP     1   /* = rs + log                                   */

@@ -58,6 +58,7 @@ class _TableSet(object):
                     d.lengths = lengths[i].data_ptr()
                 d.touch = owner.touch[name].data_ptr()
                 d.vocab = owner.params[name].shape[0]
+                assert d.vocab < (1 << 26), 'backward plan packs (attribute, row) in 32 bits: vocab < 2^26'
                 d.kind = kind
                 self.names.append(name)
                 self.bias_names.append(bname if with_bias else None)

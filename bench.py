@@ -34,7 +34,7 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--loss', default='mw')
@@ -77,7 +77,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '100'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -269,7 +269,6 @@ def main():
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    _lib.timeline = []
     l0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -278,7 +277,6 @@ def main():
     ev1.record()
     barrier()
     launches = _lib.launch_count - l0
-    tl, _lib.timeline = _lib.timeline, None
     ms_total = ev0.elapsed_time(ev1)
     # ---------------- e2e: host ids -> H2D -> step -> loss D2H -------------------------
     for s in range(min(a.warmup, 5)):
@@ -295,6 +293,13 @@ def main():
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop()
+    # ---------------- per-kernel CUDA-event durations (separate pass: the event pairs would
+    # otherwise perturb `value`); same batches, same stream -------------------------------
+    _lib.timeline = []
+    for s in range(a.warmup, nb):
+        run_step(u_dev[s], i_dev[s], False)
+    barrier()
+    tl, _lib.timeline = _lib.timeline, None
 
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)

@@ -49,10 +49,15 @@ SIGNATURES = {
     'arx_bwd_plan_end': [vp, BwdPlan, vp],
     'arx_pool_bwd_plan': [vp, i32, vp, i64, i32, BwdPlan, vp],
     'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
-    'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, vp],
+    'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, i32, vp],
     'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
     'arx_gemm_tc': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
-    'arx_transpose': [vp, i64, i64, vp, vp],
+    'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
+    'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
+    'arx_sum_over_steps': [vp, i64, i64, i32, f32, vp, vp],
+    'arx_transpose': [vp, i64, i64, vp, i32, vp],
+    'arx_round_tf32': [vp, vp, i64, vp],
     'arx_colsum': [vp, i64, i64, i64, vp, vp],
     'arx_loss_rows': [vp, i64, i64, i64, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, vp, vp],
     'arx_rowdot_fwd': [vp, vp, vp, i64, i32, vp, vp],
@@ -127,19 +132,35 @@ _MAY_BE_UNSUPPORTED = ('arx_gemm_tc',)
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 
-def gemm(A, B, C, m, n, k, trans_a, trans_b, bias=None, alpha=1.0, beta=0.0):
+ROUND_LIMIT = 1 << 26   # elements; larger operands go to the tensor core un-rounded (truncated)
+
+
+def _rounded(X, numel):
+    if numel > ROUND_LIMIT:
+        return X
+    Y = torch.empty(numel, dtype=torch.float32, device=X.device)
+    call('arx_round_tf32', X.data_ptr(), Y.data_ptr(), numel)
+    return Y
+
+
+def gemm(A, B, C, m, n, k, trans_a, trans_b, bias=None, alpha=1.0, beta=0.0, a_ready=False, b_ready=False):
     """C = alpha * op(A) op(B) + bias: tensor cores (tcgen05, tf32) when TMA can describe the
     operands, else the exact-fp32 SIMT kernel.  Both are this library's own CUDA kernels."""
     if not exact_fp32 and k % 4 == 0 and k > 0:
         # the tensor-core kernel takes K-major operands: A [m,k], B [n,k]; an operand stored the
         # other way round is staged through arx_transpose first (small next to the contraction)
-        Ak, Bk = A, B
+        # Operands are rounded to the nearest tf32 on the way (for free inside the transpose, one
+        # extra elementwise pass otherwise; skipped for operands beyond ROUND_LIMIT elements).
         if trans_a:
             Ak = torch.empty((m, k), dtype=torch.float32, device=A.device)
-            call('arx_transpose', A.data_ptr(), k, m, Ak.data_ptr())
+            call('arx_transpose', A.data_ptr(), k, m, Ak.data_ptr(), 1)
+        else:
+            Ak = A if a_ready else _rounded(A, m * k)
         if not trans_b:
             Bk = torch.empty((n, k), dtype=torch.float32, device=B.device)
-            call('arx_transpose', B.data_ptr(), k, n, Bk.data_ptr())
+            call('arx_transpose', B.data_ptr(), k, n, Bk.data_ptr(), 1)
+        else:
+            Bk = B if b_ready else _rounded(B, n * k)
         if call('arx_gemm_tc', Ak.data_ptr(), Bk.data_ptr(), C.data_ptr(), m, n, k, 0, 1, ptr(bias),
                 alpha, beta) == 0:
             return

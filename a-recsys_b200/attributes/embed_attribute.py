@@ -169,6 +169,11 @@ class EmbeddingAttribute(object):
             else:
                 i2l = np.full(n_items, -1, dtype=np.int32)
                 i2l[ids] = np.arange(V, dtype=np.int32)
+                if isinstance(item_ind2logit_ind, dict):
+                    # extra entries the runners add, e.g. START_ID -> logit 0 (lstm/run.py:276-278)
+                    for k, v in item_ind2logit_ind.items():
+                        if 0 <= k < n_items and i2l[k] < 0:
+                            i2l[k] = v
             self.item2logit_dev = torch.from_numpy(i2l).to(self.device)
         self.sampled_ids = None
         self.sampled_pos_dev = None
@@ -541,8 +546,11 @@ class EmbeddingAttribute(object):
             bias = torch.cat(biases, 0) if any_bias else None
         return arena, bias
 
-    def sparse_sumsq(self, out):
-        """Add sum over IndexedSlices values of g^2 (clip_by_global_norm term) into out[0]."""
+    def sparse_sumsq(self, out, dense_semantics=()):
+        """Add the table-gradient terms of clip_by_global_norm into out[0].  Table sets named in
+        `dense_semantics` also feed the scoring matmul, so TF holds their gradient as ONE dense
+        tensor (duplicates merged before the norm); the others are IndexedSlices (norm over the
+        un-merged slices)."""
         for ts in self.sets.values():
             if not ts.pending:
                 continue
@@ -550,7 +558,7 @@ class EmbeddingAttribute(object):
             arena, bias = self._arena(ts.pending)
             ts._ready = (plan, arena, bias)
             call('arx_pool_bwd_sumsq', ts.desc_ptr(0), self.dim, plan.c, arena.data_ptr(), arena.stride(0),
-                 ptr(bias), out.data_ptr())
+                 ptr(bias), out.data_ptr(), 1 if ts.prefix in dense_semantics else 0)
 
     def apply_gradients(self, lr, opt=OPT_ADAGRAD, grad_scale=None):
         """De-duplicated sparse optimizer step on every table set with pending gradients

@@ -29,7 +29,23 @@ __global__ void scale_mask_kernel(const float* __restrict__ x, const float* __re
     y[i] = mask ? x[i] * scale * mask[i] : x[i] * scale;
 }
 
+// fp32 -> nearest tf32 (round to nearest even on the 13 dropped mantissa bits).  The tensor core
+// TRUNCATES fp32 operands to tf32; truncation is biased (every product shrinks, ~1e-3 relative),
+// pre-rounding makes the error zero-mean and half as large.
+__device__ __forceinline__ float round_tf32(float x) {
+  unsigned int u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;          // inf / nan untouched
+  u += 0x00000fffu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xffffe000u);
+}
+
+__global__ void round_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = round_tf32(src[i]);
+}
+
 // dst[c, r] = src[r, c]; 32x32 tile through padded shared memory, coalesced both ways
+template <bool ROUND>
 __global__ void transpose_kernel(const float* __restrict__ src, long long rows, long long cols,
                                  float* __restrict__ dst) {
   __shared__ float tile[32][33];
@@ -41,7 +57,7 @@ __global__ void transpose_kernel(const float* __restrict__ src, long long rows, 
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const long long c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+    if (r < rows && c < cols) dst[c * rows + r] = ROUND ? round_tf32(tile[threadIdx.x][i]) : tile[threadIdx.x][i];
   }
 }
 
@@ -93,12 +109,22 @@ extern "C" int arx_scale_mask(const float* x, const float* mask, float scale, in
   return ARX_OK;
 }
 
-extern "C" int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream) {
+extern "C" int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, int round_tf32_out,
+                             void* stream) {
   if (!src || !dst || rows < 0 || cols < 0) return ARX_E_BADARG;
   if (rows == 0 || cols == 0) return ARX_OK;
   dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
   if (grid.y > 65535u) return ARX_E_UNSUPPORTED;
-  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, rows, cols, dst);
+  if (round_tf32_out) transpose_kernel<true><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, rows, cols, dst);
+  else transpose_kernel<false><<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(src, rows, cols, dst);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+extern "C" int arx_round_tf32(const float* src, float* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0) return ARX_E_BADARG;
+  if (n == 0) return ARX_OK;
+  round_tf32_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

@@ -708,7 +708,7 @@ pool_bwd_apply2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, in
 __global__ void __launch_bounds__(256)
 pool_bwd_sumsq_kernel(int dim, arx_bwd_plan plan, const float* __restrict__ dout,
                       long long dout_stride, const float* __restrict__ dbias,
-                      const arx_attr_desc* __restrict__ g_attrs, float* __restrict__ sumsq) {
+                      const arx_attr_desc* __restrict__ g_attrs, float* __restrict__ sumsq, int merged) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -719,6 +719,20 @@ pool_bwd_sumsq_kernel(int dim, arx_bwd_plan plan, const float* __restrict__ dout
     const int base = plan.row_base[u];
     const int cnt = plan.row_cnt[u];
     const bool has_bias = dbias != nullptr && (g_attrs == nullptr || g_attrs[f].bias != nullptr);
+    if (merged) {            // dense-gradient semantics: duplicates are summed BEFORE the norm
+      for (int c = lane; c < dim; c += 32) {
+        float g = 0.f;
+        for (int k = 0; k < cnt; ++k)
+          g = fmaf(plan.bucket_w[base + k], __ldg(dout + (size_t)plan.bucket_src[base + k] * dout_stride + c), g);
+        part = fmaf(g, g, part);
+      }
+      if (has_bias && lane == 0) {
+        float gb = 0.f;
+        for (int k = 0; k < cnt; ++k) gb = fmaf(plan.bucket_w[base + k], dbias[plan.bucket_src[base + k]], gb);
+        part = fmaf(gb, gb, part);
+      }
+      continue;
+    }
     for (int k = 0; k < cnt; ++k) {
       const int src = plan.bucket_src[base + k];
       const float w = plan.bucket_w[base + k];
@@ -881,10 +895,11 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
 }
 
 extern "C" int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_plan plan, const float* dout,
-                                  int64_t dout_stride, const float* dbias, float* sumsq, void* stream) {
+                                  int64_t dout_stride, const float* dbias, float* sumsq, int merged,
+                                  void* stream) {
   if (!dout || !sumsq || dim < 1 || !plan_args_ok(plan)) return ARX_E_BADARG;
   pool_bwd_sumsq_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(
-      dim, plan, dout, (long long)dout_stride, dbias, attrs, sumsq);
+      dim, plan, dout, (long long)dout_stride, dbias, attrs, sumsq, merged);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

@@ -127,10 +127,13 @@ int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int dim,
                        const float* dbias, float lr, const float* grad_scale_dev,
                        int opt, float* rows_out, float* bias_rows_out, void* stream);
 
-/* sum over occurrences of ||w * dOut[row]||^2 (+ bias part) — the IndexedSlices term of
- * tf.clip_by_global_norm (lstm/seqModel.py:180); accumulates into *sumsq (device). */
+/* Squared-norm term of tf.clip_by_global_norm (lstm/seqModel.py:180), accumulated into *sumsq
+ * (device).  merged = 0: IndexedSlices semantics, sum over OCCURRENCES of ||w * dOut[row]||^2
+ * (tables reached only through lookups; TF does not merge duplicate slices for the norm).
+ * merged = 1: dense-gradient semantics, sum over unique rows of ||sum_k w_k dOut[row_k]||^2
+ * (tables that also feed the scoring matmul get a dense gradient in TF). */
 int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_plan plan, const float* dout,
-                       int64_t dout_stride, const float* dbias, float* sumsq, void* stream);
+                       int64_t dout_stride, const float* dbias, float* sumsq, int merged, void* stream);
 
 /* K3/K4 dense contraction  C[m,n] = alpha * A[m,k] * op(B) + bias  (fp32 in/out).
  * trans_b = 1: B is [n,k] (scores = U * P^T, embed_attribute.py:171,188 after the
@@ -148,8 +151,14 @@ int arx_gemm_tc(const float* A, const float* B, float* C, int64_t m, int64_t n, 
                 int trans_a, int trans_b, const float* bias_n, float alpha, float beta,
                 void* stream);
 
-/* dst[c, r] = src[r, c] (fp32).  Stages an MN-major operand K-major for arx_gemm_tc. */
-int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, void* stream);
+/* dst[c, r] = src[r, c] (fp32).  Stages an MN-major operand K-major for arx_gemm_tc;
+ * round_tf32_out != 0 also rounds to the nearest tf32 (see arx_round_tf32). */
+int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, int round_tf32_out,
+                  void* stream);
+/* dst = nearest-even tf32 of src (13 low mantissa bits cleared).  tcgen05 kind::tf32 truncates
+ * fp32 operands, which is biased; pre-rounding halves the error and makes it zero-mean, keeping
+ * logits within the north star's 1e-3 of the fp32 reference. */
+int arx_round_tf32(const float* src, float* dst, int64_t n, void* stream);
 
 /* out[c] = sum_r x[r, c] — the item-bias gradient: column sums of d(loss)/d(scores)
  * (the `+ i_biases` terms of embed_attribute.py:171,188). */
@@ -194,6 +203,27 @@ int arx_rowdot_fwd(const float* U, const float* P, const float* beta, int64_t mb
                    float* out, void* stream);
 int arx_rowdot_bwd(const float* U, const float* P, const float* dts, int64_t mb, int dim,
                    float* dU_accum, float* dP, void* stream);
+
+/* K8 — TF-1.0 LSTMCell pointwise stages (lstm/seqModel.py:99-103; gate order i, j, f, o;
+ * c' = sigmoid(f + forget_bias) c + sigmoid(i) tanh(j); h' = sigmoid(o) tanh(c')).  The gate
+ * pre-activations [x, h] W + b are produced by arx_gemm_tc (x-projection of all T steps as one
+ * contraction, h_{t-1} W_h accumulated per step with beta = 1).
+ * fwd: Z [mb,4H] pre-activations in -> activated gates out (kept for the adjoint); c_prev may be
+ *      NULL (zero initial state, seqModel.py:468).
+ * bwd: G [mb,4H] activated gates in -> dZ out; dh = dh_out + dh_rec (either may be NULL),
+ *      dc_next may be NULL; writes dc_prev. */
+int arx_lstm_gates_fwd(float* Z, const float* c_prev, float* c, float* h, int64_t mb, int H,
+                       float forget_bias, void* stream);
+int arx_lstm_gates_bwd(float* G, const float* c_prev, const float* c, const float* dh_out,
+                       const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
+                       void* stream);
+/* K9 — LSTM / CBOW input mixing: y[r,:] = a*x1[r,:] + b*x2[r % rep,:] (reduce_mean([user_embed,
+ * item_embed], 0), lstm/seqModel.py:155; x2 broadcast over the T steps) and the adjoint of the
+ * broadcast: out[r,:] = scale * sum_t x[t*rep + r,:]. */
+int arx_axpby_rows(const float* x1, const float* x2_rows, float a, float b, int64_t rows,
+                   int64_t rep, int dim, float* y, void* stream);
+int arx_sum_over_steps(const float* x, int64_t T, int64_t rep, int dim, float scale, float* out,
+                       void* stream);
 
 /* K10 — tf.nn.top_k(sorted=True) over materialised scores (hmf/hmf_model.py:154):
  * descending, ties -> lower index. idx_out [mb,k] int32, val_out [mb,k] or NULL. */

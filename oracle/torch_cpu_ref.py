@@ -216,3 +216,149 @@ class TorchRefHMF(object):
                 self.acc[k] += g * g
                 self.p[k] -= self.lr * g / torch.sqrt(self.acc[k])
         return float(loss)
+
+
+class TorchRefSeq(TorchRefHMF):
+    """lstm/seqModel.py:24-604 restated with autograd: inputs = mean(user, item) (or the concat
+    projections), DropoutWrapper(in) -> LSTMCell -> DropoutWrapper(out), static unroll from a zero
+    state, per-step literal get_prediction + loss, sequence_loss, clip_by_global_norm, Adagrad/SGD.
+    params additionally hold 'lstm_w' [d_in+H, 4H], 'lstm_b' [4H] (+ 'w_input_user'/'w_input_item')."""
+
+    def __init__(self, *a, size=8, use_concat=False, no_user_id=False, no_input_item_feature=False,
+                 max_gradient_norm=5.0, withAdagrad=True, item_output=False, **kw):
+        super(TorchRefSeq, self).__init__(*a, **kw)
+        self.size, self.use_concat, self.no_user_id = size, use_concat, no_user_id
+        self.no_input_item_feature = no_input_item_feature
+        self.clip, self.withAdagrad, self.item_output = max_gradient_norm, withAdagrad, item_output
+        self.slices = []
+
+    def _emb(self, prefix, att, inds, concat, no_id=False, no_attribute=False):
+        """_get_embedded (embed_attribute.py:350-417) keeping every gathered block as a leaf-like
+        tensor so that the IndexedSlices values of tf.gradients can be read back."""
+        inds = np.asarray(inds, dtype=np.int64)
+        mb = len(inds)
+        if no_id and att.num_features_cat == 1:
+            d = self.p['%sembed_cat_0' % prefix].shape[1]
+            return torch.zeros((mb, d), dtype=self.dtype)
+        outs = []
+        n1 = 1 if no_attribute else att.num_features_cat
+        n2 = 0 if no_attribute else att.num_features_mulhot
+        for i in range(n1):
+            if no_id and i == 0:
+                continue
+            name = '%sembed_cat_%d' % (prefix, i)
+            tok = torch.from_numpy(att.features_cat[i][inds].astype(np.int64))
+            rows = self.p[name].index_select(0, tok)
+            if rows.requires_grad:
+                rows.retain_grad()
+            self.slices.append((name, rows))
+            outs.append(rows)
+        for i in range(n2):
+            name = '%sembed_mulhot_%d' % (prefix, i)
+            idx, seg, l = _flat(att, i, inds)
+            rows = self.p[name].index_select(0, idx)
+            if rows.requires_grad:
+                rows.retain_grad()
+            self.slices.append((name, rows))
+            outs.append(seg_sum(rows, seg, mb) / torch.from_numpy(l).to(self.dtype).reshape(mb, 1))
+        return torch.cat(outs, 1) if concat else torch.stack(outs, 0).mean(0)
+
+    def _pred(self, u, pool):
+        pre = 'item_output' if self.item_output else 'item'
+        ia = self.ia
+        cat, val, seg, leng = self.full if pool == 'full' else self.sampled
+        V = self.V if pool == 'full' else self.n_sampled
+        innerps = []
+        for i in range(ia.num_features_cat):
+            innerp = self.p['%sembed_cat_%d' % (pre, i)] @ u.t() + self.p['%s_bias_cat_%d' % (pre, i)]
+            innerps.append(innerp.index_select(0, cat[i]))
+        for i in range(ia.num_features_mulhot):
+            innerp = self.p['%sembed_mulhot_%d' % (pre, i)] @ u.t() + self.p['%s_bias_mulhot_%d' % (pre, i)]
+            innerps.append(seg_sum(innerp.index_select(0, val[i]), seg[i], V) / leng[i])
+        return torch.stack(innerps, 0).mean(0).t()
+
+    def _tscore(self, u, inds):
+        pre = 'item_output' if self.item_output else 'item'
+        outs, bias = self.get_embedded(pre, self.ia, inds, True)
+        return (u * torch.stack(outs, 0).mean(0)).sum(1) + bias
+
+    def forward_seq(self, users, item_inputs, targets, weights, forward_only=False, masks=None):
+        T, mb = len(item_inputs), len(users)
+        keep = 1.0 if forward_only else self.keep_prob
+        self.slices = []
+        if self.use_concat:
+            ue = self._emb('user', self.ua, users, True, no_id=self.no_user_id)
+            uproj = ue @ self.p['w_input_user']
+        else:
+            ue = self._emb('user', self.ua, users, False, no_id=self.no_user_id)
+        W, b = self.p['lstm_w'], self.p['lstm_b']
+        H = self.size
+        h = torch.zeros((mb, H), dtype=self.dtype)
+        c = torch.zeros((mb, H), dtype=self.dtype)
+        eff = 'warp' if (self.loss == 'mw' and forward_only) else self.loss
+        num = torch.zeros(mb, dtype=self.dtype)
+        den = torch.zeros(mb, dtype=self.dtype)
+        mask = None
+        if eff != 'ce':
+            mask = self.build_mask(list(users), eff, forward_only)
+        for t in range(T):
+            if self.use_concat:
+                ie = self._emb('item', self.ia, item_inputs[t], True, no_attribute=self.no_input_item_feature)
+                x = uproj + ie @ self.p['w_input_item']
+            else:
+                ie = self._emb('item', self.ia, item_inputs[t], False, no_attribute=self.no_input_item_feature)
+                x = torch.stack([ue, ie], 0).mean(0)
+            x = self._drop(x, keep, masks[0][t] if masks is not None else None)
+            z = torch.cat([x, h], 1) @ W + b
+            i, j, f, o = torch.split(z, H, dim=1)
+            c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out = self._drop(h, keep, masks[1][t] if masks is not None else None)
+            wt = torch.as_tensor(np.asarray(weights[t]), dtype=self.dtype)
+            if eff == 'mw':
+                logits = self._pred(out, 'sampled')
+                bl = self.compute_loss(logits, self._tscore(out, targets[t]), 'mw', mask)
+            else:
+                logits = self._pred(out, 'full')
+                tg = torch.as_tensor([self.i2l[int(v)] for v in targets[t]], dtype=torch.int64)
+                bl = self.compute_loss(logits, tg, eff, mask)
+            num = num + bl * wt
+            den = den + wt
+        return (num / (den + 1e-12)).sum()
+
+    def step_seq(self, users, item_inputs, targets, weights, item_sampled=None, forward_only=False, masks=None):
+        if item_sampled is not None and self.loss == 'mw':
+            self.pass_sampled_items(item_sampled)
+        if forward_only:
+            with torch.no_grad():
+                return float(self.forward_seq(users, item_inputs, targets, weights, True, masks))
+        for v in self.p.values():
+            v.grad = None
+        loss = self.forward_seq(users, item_inputs, targets, weights, False, masks)
+        loss.backward()
+        pre = 'item_output' if self.item_output else 'item'
+        # tables reached ONLY through lookups keep IndexedSlices gradients: their norm is taken over
+        # the un-merged slice values; every other gradient is dense (SURVEY Appendix C)
+        sparse_only = set(n for n, _ in self.slices if not n.startswith(pre + 'embed'))
+        sumsq = 0.0
+        for k, v in self.p.items():
+            if v.grad is None or k in sparse_only:
+                continue
+            sumsq += float((v.grad * v.grad).sum())
+        for n, rows in self.slices:
+            if n in sparse_only and rows.grad is not None:
+                sumsq += float((rows.grad * rows.grad).sum())
+        norm = sumsq ** 0.5
+        scale = self.clip / max(norm, self.clip)
+        self.last_gnorm = norm
+        with torch.no_grad():
+            for k, v in self.p.items():
+                if v.grad is None:
+                    continue
+                g = v.grad * scale
+                if self.withAdagrad:
+                    self.acc[k] += g * g
+                    v -= self.lr * g / torch.sqrt(self.acc[k])
+                else:
+                    v -= self.lr * g
+        return float(loss)

@@ -22,7 +22,7 @@ def _run(M, N, K, ta, tb, bias=True, alpha=1.0):
     C = torch.full((M, N), 7.0, device='cuda')
     n0 = _lib.launch_count
     _lib.gemm(dA, dB, C, M, N, K, int(ta), int(tb), db, alpha, 0.0)     # K-major natively, else staged by arx_transpose
-    assert _lib.launch_count - n0 == 1 + int(bool(ta)) + int(not tb), 'tensor-core path not taken'
+    assert _lib.launch_count - n0 == 3, 'tensor-core path not taken (expected 2 staging passes + arx_gemm_tc)'
     got = C.cpu().numpy()
     scale = np.abs(ref).max()
     err = np.abs(got - ref).max() / scale

@@ -1,0 +1,47 @@
+"""CBOW window batcher (reference: word2vec/data_iterator.py:108-169), vectorised.
+
+The training corpus is the concatenation of every user's time-ordered items with a PAD event
+before each user (word2vec/run_w2v.py:118-131).  For every non-PAD event (u, o) the reference keeps
+a deque of the previous `skip_window` stream events and draws `ni` of them (without replacement
+once the user has >= ni earlier events in the window, with replacement before) as the inputs —
+drawn from the stream window, so they may belong to the previous user or be the PAD pseudo-item,
+exactly as in the reference.  Same distribution, NumPy instead of a Python deque per event.
+"""
+import numpy as np
+
+
+class DataIterator(object):
+    def __init__(self, seq, end_ind, batch_size, n_skips, window, sequence):
+        seq = np.asarray(seq, dtype=np.int64).reshape(-1, 2)
+        self.users, self.items = seq[:, 0], seq[:, 1]
+        self.l_seq = len(seq)
+        self.end_ind = end_ind
+        self.batch_size = batch_size
+        self.num_skips = n_skips
+        self.skip_window = window
+        if sequence:
+            print('error: not implemented')
+            exit(1)
+        is_pad = self.items == end_ind
+        # events since the user's PAD marker (1 for the first real event), capped at the window
+        idx = np.arange(self.l_seq)
+        last_pad = np.maximum.accumulate(np.where(is_pad, idx, -1))
+        self.u_seq_len = np.minimum(idx - last_pad, window)
+        self.targets = np.nonzero(~is_pad)[0]
+        self.cursor = int(np.searchsorted(self.targets, window))      # first centre = stream position `window`
+
+    def get_next_cbow(self):
+        mb, ni, c = self.batch_size, self.num_skips, self.skip_window
+        nt = len(self.targets)
+        while True:
+            sel = self.targets[(self.cursor + np.arange(mb)) % nt]
+            self.cursor = (self.cursor + mb) % nt
+            with_repl = self.u_seq_len[sel] < ni
+            offs = np.argsort(np.random.random((mb, c)), axis=1)[:, :ni] if ni <= c else \
+                np.random.randint(0, c, (mb, ni))
+            offs_r = np.random.randint(0, c, (mb, ni))
+            offs = np.where(with_repl[:, None], offs_r, offs)
+            pos = (sel[:, None] - c + offs) % self.l_seq
+            i_items = self.items[pos]                                   # [mb, ni]
+            yield (self.users[sel].astype(np.int32), [i_items[:, k].astype(np.int32) for k in range(ni)],
+                   self.items[sel].astype(np.int32))

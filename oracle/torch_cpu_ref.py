@@ -362,3 +362,50 @@ class TorchRefSeq(TorchRefHMF):
                 else:
                     v -= self.lr * g
         return float(loss)
+
+
+class TorchRefCbow(TorchRefSeq):
+    """word2vec/cbow_model.py:76-136 restated with autograd: h = dropout(mean(user, mean_k item_k)),
+    literal get_prediction over the (separate) output tables, loss, Adagrad."""
+
+    def __init__(self, *a, ni=2, **kw):
+        super(TorchRefCbow, self).__init__(*a, **kw)
+        self.ni = ni
+
+    def step_cbow(self, users, item_inputs, item_outputs, item_sampled=None, forward_only=False, mask=None):
+        if item_sampled is not None and self.loss == 'mw':
+            self.pass_sampled_items(item_sampled)
+        n_input = max(self.ni, 1)
+        keep = 1.0 if forward_only else self.keep_prob
+
+        def fwd():
+            self.slices = []
+            ue = self._emb('user', self.ua, users, False)
+            its = torch.stack([self._emb('item', self.ia, item_inputs[k], False) for k in range(n_input)], 0).mean(0)
+            if forward_only and self.ni == 0:
+                x = ue
+            else:
+                x = torch.stack([ue, its], 0).mean(0)
+            h = self._drop(x, keep, mask)
+            eff = 'warp' if (self.loss == 'mw' and forward_only) else self.loss
+            m = self.build_mask(list(users), eff, forward_only) if eff != 'ce' else None
+            if eff == 'mw':
+                bl = self.compute_loss(self._pred(h, 'sampled'), self._tscore(h, item_outputs), 'mw', m)
+            else:
+                tg = torch.as_tensor([self.i2l[int(v)] for v in item_outputs], dtype=torch.int64)
+                bl = self.compute_loss(self._pred(h, 'full'), tg, eff, m)
+            return bl.mean()
+        if forward_only:
+            with torch.no_grad():
+                return float(fwd())
+        for v in self.p.values():
+            v.grad = None
+        loss = fwd()
+        loss.backward()
+        with torch.no_grad():
+            for k, v in self.p.items():
+                if v.grad is None:
+                    continue
+                self.acc[k] += v.grad * v.grad
+                v -= self.lr * v.grad / torch.sqrt(self.acc[k])
+        return float(loss)

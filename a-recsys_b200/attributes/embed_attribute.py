@@ -57,16 +57,18 @@ class _TableSet(object):
                     d.starts = starts[i].data_ptr()
                     d.lengths = lengths[i].data_ptr()
                 d.touch = owner.touch[name].data_ptr()
-                d.vocab = owner.params[name].shape[0]
+                d.vocab = owner.touch[name].shape[0]            # global vocabulary (touch is global-sized)
                 assert d.vocab < (1 << 26), 'backward plan packs (attribute, row) in 32 bits: vocab < 2^26'
                 d.kind = kind
+                if owner.shard is not None:
+                    d.reserved = (owner.shard[0] << 16) | owner.shard[1]
                 self.names.append(name)
                 self.bias_names.append(bname if with_bias else None)
                 k += 1
         raw = np.frombuffer(bytes(descs), dtype=np.uint8).copy()
         self.descs_dev = torch.from_numpy(raw).to(owner.device)
         self.desc_size = ctypes.sizeof(AttrDesc)
-        self.total_vocab = sum(owner.params[n].shape[0] for n in self.names)
+        self.total_vocab = sum(owner.touch[n].shape[0] for n in self.names)
         self.max_len = [1] * self.n_cat + [int(att.mulhot_lengths[i].max()) for i in range(self.n_mul)]
         self.pending = []          # (attr_begin, n_attr, ids, mode, dout[n, w], dbias or None, plan_key)
         self.plans = {}            # plan_key -> (_Plan, rows)
@@ -110,10 +112,12 @@ class _Plan(object):
 class EmbeddingAttribute(object):
     def __init__(self, user_attributes, item_attributes, mb, n_sampled, input_steps=0,
                  item_output=False, item_ind2logit_ind=None, logit_ind2item_ind=None,
-                 indices_item=None, devices=['/gpu:0'], device=None, seed=None, params=None):
+                 indices_item=None, devices=['/gpu:0'], device=None, seed=None, params=None, shard=None):
         if not torch.cuda.is_available():
             raise RuntimeError('arecsys_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         _lib.load()
+        # shard = (G, r): this GPU stores rows t with t % G == r of every table
+        self.shard = shard if (shard is not None and shard[0] > 1) else None
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.user_attributes = user_attributes
         self.item_attributes = item_attributes
@@ -194,9 +198,20 @@ class EmbeddingAttribute(object):
         else:
             # tf.get_variable default in TF1.0: glorot_uniform; unseeded there.
             limit = math.sqrt(6.0 / (shape[0] + shape[1]))
+            if self.shard is not None and shape[0] > (1 << 20):
+                # large sharded table: draw only the local rows (a 10^7-row global draw costs 5 GB)
+                G, r = self.shard
+                local = (shape[0] - r + G - 1) // G
+                w = (torch.rand((local, shape[1]), generator=gen, dtype=torch.float32) * 2 - 1) * limit
+                self.params[name] = w.to(self.device).contiguous()
+                self.accs[name] = torch.full(tuple(w.shape), ADAGRAD_INIT_ACC, dtype=torch.float32, device=self.device)
+                return
             w = (torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * limit
+        if self.shard is not None:
+            G, r = self.shard
+            w = w[r::G]                       # the global initialisation, rows this GPU owns
         self.params[name] = w.to(self.device).contiguous()
-        self.accs[name] = torch.full(shape, ADAGRAD_INIT_ACC, dtype=torch.float32, device=self.device)
+        self.accs[name] = torch.full(tuple(w.shape), ADAGRAD_INIT_ACC, dtype=torch.float32, device=self.device)
 
     def _embedded(self, att, prefix, gen, params):
         for tag, n, V in (('cat', att.num_features_cat, att._embedding_classes_list_cat),
@@ -596,9 +611,10 @@ class EmbeddingAttribute(object):
         attr = plan.uniq_attr[:nu].long()
         for f, name in enumerate(ts.names):
             sel = attr == f
-            grads[name][tok[sel]] = rows[:nu][sel]
+            lt = tok[sel] // self.shard[0] if self.shard is not None else tok[sel]
+            grads[name][lt] = rows[:nu][sel]
             if ts.bias_names[f] and bias is not None:
-                bgrads[ts.bias_names[f]][tok[sel], 0] = brow[:nu][sel]
+                bgrads[ts.bias_names[f]][lt, 0] = brow[:nu][sel]
         ts.pending = []
         grads.update(bgrads)
         return grads

@@ -74,6 +74,16 @@ __device__ __forceinline__ void stage_descs(arx_attr_desc* s_attrs, const arx_at
   __syncthreads();
 }
 
+// Row sharding: arx_attr_desc.reserved = (G << 16) | r means this GPU stores only the
+// rows t with t % G == r, at local row t / G (cyclic: balances the Zipf head).  0 = unsharded.
+// Kernels skip the rows they do not own; the host sums / exchanges the partial results.
+struct Shard { int G, r; };
+__device__ __forceinline__ Shard shard_of(const arx_attr_desc& a) {
+  Shard s; s.G = a.reserved >> 16; s.r = a.reserved & 0xffff; return s;
+}
+__device__ __forceinline__ bool owns(const Shard& s, int tok) { return s.G <= 1 || (tok % s.G) == s.r; }
+__device__ __forceinline__ int local_row(const Shard& s, int tok) { return s.G <= 1 ? tok : tok / s.G; }
+
 // Lane f < n_attr fetches the bag (start, length) of attribute f for entity e.
 // A categorical attribute is a bag of length 1 starting at e inside features_cat.
 __device__ __forceinline__ void fetch_bags(const arx_attr_desc* s_attrs, int n_attr, int lane, int e,
@@ -90,78 +100,7 @@ __device__ __forceinline__ void fetch_bags(const arx_attr_desc* s_attrs, int n_a
 }
 
 // ------------------------------------------------------------------ forward ---------
-// One warp per entity.  GW lanes cover one row chunk (GW*VEC floats); the 32/GW lane
-// groups take different tokens of the bag and are reduced with shuffles.
-template <int GW, int VEC>
-__global__ void __launch_bounds__(256)
-pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
-                const int* __restrict__ ids, long long n, float* __restrict__ out,
-                long long out_stride, int mode, float* __restrict__ bias_out) {
-  using VT = typename V<VEC>::T;
-  __shared__ arx_attr_desc s_attrs[kMaxAttr];
-  stage_descs(s_attrs, g_attrs, n_attr);
-  constexpr int NG = 32 / GW;
-  const int lane = threadIdx.x & 31;
-  const int g = lane / GW, l = lane % GW;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nvec = dim / VEC;
-  const float Ff = (float)n_attr;
-
-  for (long long ei = warp0; ei < n; ei += nwarps) {
-    const int e = __ldg(ids + ei);
-    int my_s, my_L;
-    fetch_bags(s_attrs, n_attr, lane, e, my_s, my_L);
-    float bias_tot = 0.f;
-    for (int c0 = 0; c0 < nvec; c0 += GW) {
-      const int col = c0 + l;
-      const bool colok = col < nvec;
-      VT tot = V<VEC>::zero();
-      for (int f = 0; f < n_attr; ++f) {
-        const int s = __shfl_sync(ARX_FULL_MASK, my_s, f);
-        const int L = __shfl_sync(ARX_FULL_MASK, my_L, f);
-        const float* __restrict__ table = s_attrs[f].table;
-        const int* __restrict__ values = s_attrs[f].values;
-        const float* __restrict__ bias = s_attrs[f].bias;
-        const bool want_bias = (c0 == 0) && (bias_out != nullptr) && (bias != nullptr);
-        VT acc = V<VEC>::zero();
-        float bsum = 0.f;
-        for (int j0 = 0; j0 < L; j0 += 32) {
-          const int cnt = min(32, L - j0);
-          const int tok = (lane < cnt) ? __ldg(values + s + j0 + lane) : 0;
-          if (want_bias && lane < cnt) bsum += __ldg(bias + tok);
-          for (int jj0 = 0; jj0 < cnt; jj0 += NG * kRowsInFlight) {
-            VT v[kRowsInFlight];
-#pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) {
-              const int jj = jj0 + u * NG + g;
-              const int t = __shfl_sync(ARX_FULL_MASK, tok, jj & 31);
-              v[u] = (jj < cnt && colok) ? V<VEC>::ldg(table + (size_t)t * dim + (size_t)col * VEC)
-                                         : V<VEC>::zero();
-            }
-#pragma unroll
-            for (int u = 0; u < kRowsInFlight; ++u) V<VEC>::add(acc, v[u]);
-          }
-        }
-#pragma unroll
-        for (int o = GW; o < 32; o <<= 1) V<VEC>::add(acc, V<VEC>::shfl_xor(acc, o));
-        const float Lf = (float)L;
-        acc = V<VEC>::div(acc, Lf);                      // tf.div(embedded_sum, lengs)  :400
-        if (want_bias) bias_tot += warp_sum(bsum) / Lf;  // :404-406
-        if (mode == ARX_POOL_MEAN) {
-          V<VEC>::add(tot, acc);
-        } else if (g == 0 && colok) {
-          V<VEC>::st(out + ei * out_stride + (size_t)f * dim + (size_t)col * VEC, acc);
-        }
-      }
-      if (mode == ARX_POOL_MEAN && g == 0 && colok)
-        V<VEC>::st(out + ei * out_stride + (size_t)col * VEC, V<VEC>::div(tot, Ff));  // reduce_mean :219,:235
-    }
-    if (bias_out != nullptr && lane == 0) bias_out[ei] = bias_tot / Ff;               // :412
-  }
-}
-
-// ---- v2 forward: one warp per (entity, attribute) pair -------------------------------
+// one warp per (entity, attribute) pair
 // A CTA owns EPB consecutive entities; its 8 warps stride over the EPB*n_attr bags, each
 // bag is gathered with >= 8 rows in flight, divided by its length and parked in shared
 // memory; after a barrier the attribute mean (fixed order => deterministic) is written
@@ -169,7 +108,7 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
 // pool still fills all 148 SMs, and no warp walks nine dependent bags in sequence.
 template <int GW, int VEC>
 __global__ void __launch_bounds__(256)
-pool_fwd2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
+pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
                  const int* __restrict__ ids, long long n, float* __restrict__ out,
                  long long out_stride, int mode, float* __restrict__ bias_out, int epb) {
   using VT = typename V<VEC>::T;
@@ -195,6 +134,7 @@ pool_fwd2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
       const int* __restrict__ values = s_attrs[f].values;
       const float* __restrict__ bias = s_attrs[f].bias;
       const bool want_bias = (bias_out != nullptr) && (bias != nullptr);
+      const Shard sh = shard_of(s_attrs[f]);
       const float Lf = (float)L;
       float bsum = 0.f;
       for (int c0 = 0; c0 < nvec; c0 += GW) {
@@ -203,16 +143,17 @@ pool_fwd2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
         VT acc = V<VEC>::zero();
         for (int j0 = 0; j0 < L; j0 += 32) {
           const int cnt = min(32, L - j0);
-          const int tok = (lane < cnt) ? __ldg(values + s + j0 + lane) : 0;
-          if (want_bias && c0 == 0 && lane < cnt) bsum += __ldg(bias + tok);
+          int tok = (lane < cnt) ? __ldg(values + s + j0 + lane) : 0;
+          tok = owns(sh, tok) ? local_row(sh, tok) : -1;          // -1: row lives on another GPU
+          if (want_bias && c0 == 0 && lane < cnt && tok >= 0) bsum += __ldg(bias + tok);
           for (int jj0 = 0; jj0 < cnt; jj0 += NG * kRowsInFlight) {
             VT v[kRowsInFlight];
 #pragma unroll
             for (int u = 0; u < kRowsInFlight; ++u) {
               const int jj = jj0 + u * NG + g;
               const int t = __shfl_sync(ARX_FULL_MASK, tok, jj & 31);
-              v[u] = (jj < cnt && colok) ? V<VEC>::ldg(table + (size_t)t * dim + (size_t)col * VEC)
-                                         : V<VEC>::zero();
+              v[u] = (jj < cnt && colok && t >= 0) ? V<VEC>::ldg(table + (size_t)t * dim + (size_t)col * VEC)
+                                                   : V<VEC>::zero();
             }
 #pragma unroll
             for (int u = 0; u < kRowsInFlight; ++u) V<VEC>::add(acc, v[u]);
@@ -292,13 +233,14 @@ plan_count_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int
     if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
     const int* __restrict__ values = s_attrs[f].values;
     int* touch = s_attrs[f].touch;
+    const Shard sh = shard_of(s_attrs[f]);
     for (int j0 = 0; j0 < L; j0 += 32) {
       const int j = j0 + lane;
       int tok = 0;
       bool first = false;
       if (j < L) {
         tok = __ldg(values + s + j);
-        first = (atomicAdd(&touch[tok], 1) == 0);
+        if (owns(sh, tok)) first = (atomicAdd(&touch[tok], 1) == 0);
       }
       const unsigned m = __ballot_sync(ARX_FULL_MASK, first);
       if (m != 0u) {
@@ -376,8 +318,10 @@ plan_fill_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int 
     int* touch = s_attrs[f].touch;
     const float w = invF / (float)L;
     const int row = (mode == ARX_POOL_MEAN) ? (int)(row_base + ei) : (int)(row_base + ei * n_attr + f);
+    const Shard sh = shard_of(s_attrs[f]);
     for (int j = lane; j < L; j += 32) {
       const int tok = __ldg(values + s + j);
+      if (!owns(sh, tok)) continue;
       const int pos = atomicAdd(&touch[tok], 1);
       plan.bucket_src[pos] = row;
       plan.bucket_w[pos] = w;
@@ -392,96 +336,6 @@ __global__ void plan_reset_kernel(const arx_attr_desc* __restrict__ g_attrs, arx
 }
 
 // ------------------------------------------------------------------ backward apply --
-// One warp per unique (table,row): segment-sum its bucket out of dOut (L2-resident),
-// then one read-modify-write of the table row and its accumulator.
-template <int VEC>
-__global__ void __launch_bounds__(256)
-pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
-                      arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
-                      const float* __restrict__ dbias, float lr,
-                      const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
-                      float* __restrict__ bias_rows_out) {
-  using VT = typename V<VEC>::T;
-  __shared__ arx_attr_desc s_attrs[kMaxAttr];
-  stage_descs(s_attrs, g_attrs, n_attr);
-  if (plan.counters[2] != 0) return;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nvec = dim / VEC;
-  const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
-  const float gs = grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f;
-
-  for (long long u = warp0; u < nu; u += nwarps) {
-    const int tok = plan.uniq_tok[u];
-    const int f = plan.uniq_attr[u];
-    const int base = plan.row_base[u];
-    const int cnt = plan.row_cnt[u];
-    float gb = 0.f;
-    for (int c0 = 0; c0 < nvec; c0 += 32) {
-      const int col = c0 + lane;
-      const bool colok = col < nvec;
-      VT g = V<VEC>::zero();
-      for (int k0 = 0; k0 < cnt; k0 += 32) {
-        const int kc = min(32, cnt - k0);
-        int src = 0; float w = 0.f;
-        if (lane < kc) { src = __ldg(plan.bucket_src + base + k0 + lane); w = __ldg(plan.bucket_w + base + k0 + lane); }
-        if (c0 == 0 && dbias != nullptr && lane < kc) gb = fmaf(w, __ldg(dbias + src), gb);
-        for (int kk0 = 0; kk0 < kc; kk0 += kRowsInFlight) {
-          VT v[kRowsInFlight]; float wk[kRowsInFlight];
-#pragma unroll
-          for (int q = 0; q < kRowsInFlight; ++q) {
-            const int kk = kk0 + q;
-            const int sk = __shfl_sync(ARX_FULL_MASK, src, kk & 31);
-            wk[q] = __shfl_sync(ARX_FULL_MASK, w, kk & 31);
-            v[q] = (kk < kc && colok) ? V<VEC>::ldg(dout + (size_t)sk * dout_stride + (size_t)col * VEC)
-                                      : V<VEC>::zero();
-          }
-#pragma unroll
-          for (int q = 0; q < kRowsInFlight; ++q) V<VEC>::fma(g, wk[q], v[q]);
-        }
-      }
-      g = V<VEC>::mul(g, gs);
-      if (colok) {
-        const size_t off = (size_t)tok * dim + (size_t)col * VEC;
-        if (opt == ARX_OPT_ADAGRAD) {
-          float* wp = s_attrs[f].table + off;
-          float* ap = s_attrs[f].table_acc + off;
-          VT wv = V<VEC>::ld(wp), av = V<VEC>::ld(ap);
-          V<VEC>::adagrad(wv, av, g, lr);
-          V<VEC>::st(ap, av);
-          V<VEC>::st(wp, wv);
-        } else if (opt == ARX_OPT_SGD) {
-          float* wp = s_attrs[f].table + off;
-          VT wv = V<VEC>::ld(wp);
-          V<VEC>::sgd(wv, g, lr);
-          V<VEC>::st(wp, wv);
-        } else {
-          V<VEC>::st(rows_out + (size_t)u * dim + (size_t)col * VEC, g);
-        }
-      }
-    }
-    if (dbias != nullptr && s_attrs[f].bias != nullptr) {
-      gb = warp_sum(gb) * gs;
-      if (lane == 0) {
-        if (opt == ARX_OPT_ADAGRAD) {
-          float a = s_attrs[f].bias_acc[tok];
-          a = fmaf(gb, gb, a);
-          s_attrs[f].bias_acc[tok] = a;
-          s_attrs[f].bias[tok] -= lr * gb / sqrtf(a);
-        } else if (opt == ARX_OPT_SGD) {
-          s_attrs[f].bias[tok] -= lr * gb;
-        } else if (bias_rows_out != nullptr) {
-          bias_rows_out[u] = gb;
-        }
-      }
-    } else if (opt == ARX_OPT_NONE && bias_rows_out != nullptr && lane == 0) {
-      bias_rows_out[u] = 0.f;
-    }
-  }
-}
-
-// ---- v2 of the apply kernel ---------------------------------------------------------
 // (a) hot rows are reduced chunk-by-chunk by many warps (last arriver folds + updates);
 // (b) the remaining rows are taken 32 at a time: one coalesced metadata load and one
 //     first-bucket-entry load per lane, then four rows per step with their table row,
@@ -552,7 +406,7 @@ constexpr int kRowsPerStep = 4;
 
 template <int VEC>
 __global__ void __launch_bounds__(256, 2)
-pool_bwd_apply2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
+pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
                        arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
                        const float* __restrict__ dbias, float lr,
                        const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
@@ -599,8 +453,8 @@ pool_bwd_apply2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, in
     last = __shfl_sync(ARX_FULL_MASK, last, 0);
     if (!last) continue;
     __threadfence();
-    const int tok = plan.uniq_tok[u];
     const int f = plan.uniq_attr[u];
+    const int tok = local_row(shard_of(s_attrs[f]), plan.uniq_tok[u]);   // row inside this GPU's shard
     for (int c0 = 0; c0 < nvec; c0 += 32) {
       const int col = c0 + lane;
       const bool colok = col < nvec;
@@ -637,7 +491,8 @@ pool_bwd_apply2_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, in
     const int u = (int)u0 + lane;
     int tok = 0, f = 0, base = 0, cnt = 0;
     if (u < nu) {
-      tok = __ldg(plan.uniq_tok + u); f = __ldg(plan.uniq_attr + u);
+      f = __ldg(plan.uniq_attr + u);
+      tok = local_row(shard_of(s_attrs[f]), __ldg(plan.uniq_tok + u));
       base = __ldg(plan.row_base + u); cnt = __ldg(plan.row_cnt + u);
     }
     const bool light = (u < nu) && (cnt <= kHeavy);
@@ -775,7 +630,7 @@ int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* i
   const long long cap = (long long)arx_num_sms() * 32;
   const int grid = (int)(blocks > cap ? cap : blocks);
 #define ARX_FWD(GW)                                                                                  \
-  pool_fwd2_kernel<GW, VEC><<<grid, threads, smem, st>>>(attrs, n_attr, dim, ids, (long long)n, out, \
+  pool_fwd_kernel<GW, VEC><<<grid, threads, smem, st>>>(attrs, n_attr, dim, ids, (long long)n, out, \
                                                          (long long)out_stride, mode, bias_out, epb)
   if (nvec >= 32) ARX_FWD(32);
   else if (nvec >= 16) ARX_FWD(16);
@@ -885,10 +740,10 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
   const int grid = arx_num_sms() * 2;   // persistent (2 CTAs/SM): warps stride over the device-side row list
   const bool v4 = (dim % 4 == 0) && (dout_stride % 4 == 0) && (((uintptr_t)dout & 15) == 0);
   if (v4)
-    pool_bwd_apply2_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+    pool_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
                                                     dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
   else
-    pool_bwd_apply2_kernel<1><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+    pool_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
                                                     dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
   ARX_CHECK_LAUNCH();
   return ARX_OK;

@@ -76,7 +76,7 @@ class LatentProductModel(object):
                  item_ind2logit_ind=None, logit_ind2item_ind=None, loss_function='ce', GPU=None,
                  logit_size_test=None, nonlinear=None, dropout=1.0, n_sampled=None, indices_item=None,
                  dtype=torch.float32, top_N_items=100, hidden_size=500, loss_func='log',
-                 loss_exp_p=1.005, seed=None, params=None):
+                 loss_exp_p=1.005, seed=None, params=None, shard=None):
         self.user_size = user_size
         self.item_size = item_size
         self.top_N_items = top_N_items
@@ -117,7 +117,7 @@ class LatentProductModel(object):
         mb = batch_size
         m = embed_attribute.EmbeddingAttribute(user_attributes, item_attributes, mb, self.n_sampled, 0,
                                                False, item_ind2logit_ind, logit_ind2item_ind, seed=seed,
-                                               params=params)
+                                               params=params, shard=shard)
         self.att_emb = m
         self.device = m.device
         self.dense, self.dense_acc = {}, {}

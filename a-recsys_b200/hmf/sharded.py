@@ -1,0 +1,92 @@
+"""Row-sharded HMF (BASELINE config 4: HMF + WMRB `mw`, item tables sharded across up to 8 GPUs).
+
+One process per GPU.  Every table row t lives on GPU t % G with its Adagrad accumulator; each rank
+pools the rows it owns for the WHOLE global batch (the sm_100a kernels skip foreign rows), the
+partial pooled vectors are reduce-scattered so that rank r holds the complete user / target-item
+vectors of its own mb rows, scores and the loss are computed on those rows, and the gradients of
+the pooled vectors are all-gathered back so that every owner updates its rows locally.
+"""
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import POOL_MEAN, OPT_ADAGRAD, call
+from .hmf_model import LatentProductModel
+from .exchange import RowShardExchange
+
+
+class ShardedLatentProductModel(LatentProductModel):
+    def __init__(self, *a, group=None, **kw):
+        self.ex = RowShardExchange(group)
+        kw['shard'] = (self.ex.G, self.ex.r)
+        super(ShardedLatentProductModel, self).__init__(*a, **kw)
+        if self.loss_function != 'mw' or self.nonlinear in ('relu', 'tanh'):
+            raise NotImplementedError('the sharded path covers the linear HMF tower with loss mw (config 4)')
+
+    def step(self, session, user_input, item_input, neg_item_input=None, item_sampled=None,
+             item_sampled_id2idx=None, forward_only=False, recommend=False, recommend_new=False, loss=None,
+             run_op=None, run_meta=None, masks=None, sync=True):
+        """user_input / item_input: the GLOBAL batch (G*mb ids, identical on every rank);
+        rank r scores rows [r*mb, (r+1)*mb).  Returns the global mean loss."""
+        if forward_only or recommend:
+            raise NotImplementedError('sharded evaluation / recommendation is not provided yet')
+        m, ex = self.att_emb, self.ex
+        G, r, d = ex.G, ex.r, self.size
+        dev = self.device
+        m.add_input({}, user_input, item_input, item_sampled=item_sampled, item_sampled_id2idx=item_sampled_id2idx,
+                    loss='mw')
+        users_g = m.u_indices['input']
+        items_g = m._ids(item_input)
+        n_g = users_g.numel()
+        mb = n_g // G
+        S = m.sampled_ids.numel()
+        pre = m._out_prefix()
+        # ---- forward: partial pooling of owned rows, one RS + one AR --------------------------
+        fwd = torch.empty((n_g, 2 * d + 1), dtype=torch.float32, device=dev)
+        pu, _, urng = m.pool('user', users_g, POOL_MEAN, False)
+        pt, bt, irng = m.pool(pre, items_g, POOL_MEAN, True)
+        fwd[:, :d] = pu
+        fwd[:, d:2 * d] = pt
+        fwd[:, 2 * d] = bt
+        ps, bs, _ = m.pool(pre, m.sampled_ids, POOL_MEAN, True)
+        sp = torch.cat([ps, bs[:, None]], 1)
+        loc = ex.reduce_scatter_rows(fwd)
+        sp = ex.all_reduce(sp)
+        U0 = loc[:, :d].contiguous()
+        Pt = loc[:, d:2 * d].contiguous()
+        btl = loc[:, 2 * d].contiguous()
+        Ps = sp[:, :d].contiguous()
+        bsl = sp[:, d].contiguous()
+        users_l = users_g[r * mb:(r + 1) * mb].contiguous()
+        keep = self.dropout
+        u = m.dropout(U0, keep, masks[0] if masks else None)
+        dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
+        logits = torch.empty((mb, S), dtype=torch.float32, device=dev)
+        _lib.gemm(u, Ps, logits, mb, S, d, 0, 1, bsl)
+        tscore = torch.empty((mb,), dtype=torch.float32, device=dev)
+        call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), btl.data_ptr(), mb, d, tscore.data_ptr())
+        scale = self._scale(n_g)[:mb]                                   # 1 / (G*mb): global batch mean
+        bl = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=True, pos_rows=users_l)
+        loss_sum = (bl.sum() / n_g).reshape(1)
+        # ---- backward: one AR + one AG, then local sparse Adagrad --------------------------------
+        D, dts = logits, m._last_dtarget
+        dU, dPs, dbs = self._scores_backward(D, u, Ps)
+        dPt = torch.empty_like(Pt)
+        call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, d, dU.data_ptr(), dPt.data_ptr())
+        if keep != 1.0:
+            dU0 = torch.empty_like(dU)
+            call('arx_scale_mask', dU.data_ptr(), dmask.data_ptr(), 1.0 / keep, dU.numel(), dU0.data_ptr())
+        else:
+            dU0 = dU
+        dsp = ex.all_reduce(torch.cat([dPs, dbs[:, None]], 1))
+        back = ex.all_gather_rows(torch.cat([dU0, dPt, dts[:, None]], 1))
+        m.push_grad('user', urng, users_g, POOL_MEAN, back[:, :d].contiguous())
+        rng = m.sets[pre].attr_range()
+        m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, dsp[:, :d].contiguous(), dsp[:, d].contiguous())
+        m.push_grad(pre, rng, items_g, POOL_MEAN, back[:, d:2 * d].contiguous(), back[:, 2 * d].contiguous())
+        m.apply_gradients(self.learning_rate.eval(), OPT_ADAGRAD)
+        self.global_step.assign(self.global_step.eval() + 1)
+        if not sync:
+            return loss_sum
+        ex.all_reduce(loss_sum)
+        return float(loss_sum.item())

@@ -40,7 +40,7 @@ i64, i32, f32 = ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
 # name -> argtypes; every function returns int except the two info calls.
 SIGNATURES = {
-    'arx_pool_fwd': [vp, i32, i32, vp, i64, vp, i64, i32, vp, vp],
+    'arx_pool_fwd': [vp, i32, i32, vp, i64, vp, i64, i32, vp, i32, vp],
     'arx_mulhot_flat_index': [vp, i32, vp, i64, vp, vp, vp, vp],
     'arx_bwd_plan_begin': [BwdPlan, vp],
     'arx_bwd_plan_count': [vp, i32, i32, vp, i64, BwdPlan, vp],

@@ -246,7 +246,7 @@ class EmbeddingAttribute(object):
             bias_out = torch.empty((n,), dtype=torch.float32, device=self.device)
         _lib.tag = prefix
         call('arx_pool_fwd', ts.desc_ptr(a0), na, self.dim, ids.data_ptr(), n, out.data_ptr(),
-             out.stride(0), mode, ptr(bias_out) if want_bias else None)
+             out.stride(0), mode, ptr(bias_out) if want_bias else None, int(sum(ts.max_len[a0:a0 + na])))
         return out, (bias_out if want_bias else None), (a0, na)
 
     def flat_indices(self, prefix, attr, ids):
@@ -315,7 +315,11 @@ class EmbeddingAttribute(object):
     def pass_sampled_items(self, item_sampled):
         """`update_sampled`: remember the sampled pool (its CSR is read straight from the
         attribute store by the kernels, no materialisation) and the item -> pool-position map."""
-        self.sampled_ids = self._ids(item_sampled)
+        new_ids = self._ids(item_sampled)
+        if self.sampled_ids is not None and self.sampled_ids.shape == new_ids.shape:
+            self.sampled_ids.copy_(new_ids)      # in place: captured CUDA graphs keep reading this buffer
+        else:
+            self.sampled_ids = new_ids.clone()
         n_items = self.item_attributes.num_entities
         if self.sampled_pos_dev is None:
             self.sampled_pos_dev = torch.full((n_items,), -1, dtype=torch.int32, device=self.device)
@@ -324,8 +328,10 @@ class EmbeddingAttribute(object):
         self.sampled_pos_dev[self.sampled_ids.long()] = torch.arange(
             self.sampled_ids.numel(), dtype=torch.int32, device=self.device)
         self._sampled_version = getattr(self, '_sampled_version', 0) + 1
-        for k in ('mw_train', 'mw_eval'):
-            self.pos_csr.pop(k, None)
+        for k in ('mw_train', 'mw_eval'):       # masked columns = pool positions: refresh in place
+            if k in self.pos_csr:
+                items_d = self._pos_items_dev[k.split('_')[1]]
+                self.pos_csr[k][1].copy_(self.sampled_pos_dev[items_d])
         for ts in self.sets.values():
             ts.plans.pop('sampled', None)
 
@@ -429,6 +435,7 @@ class EmbeddingAttribute(object):
         self.pos_item_set_eval = pos_item_set_eval
         self.pos_csr = {}
         self._pos_host = {}
+        self._pos_items_dev = {}
 
     def _positives_host(self, which):
         """CSR over users of positive ITEM indices (host, int32), built once per item set."""
@@ -458,6 +465,9 @@ class EmbeddingAttribute(object):
         ptr_h, items_h = self._positives_host(which)
         ptr_d = torch.from_numpy(ptr_h).to(self.device)
         items_d = torch.from_numpy(items_h).to(self.device).long()
+        if not hasattr(self, '_pos_items_dev'):
+            self._pos_items_dev = {}
+        self._pos_items_dev[which] = items_d
         if kind == 'full':
             cols = self.item2logit_dev[items_d]
             # sort columns inside each user's slice: one global sort on (user, col) keys

@@ -107,7 +107,7 @@ __device__ __forceinline__ void fetch_bags(const arx_attr_desc* s_attrs, int n_a
 // with 128-bit stores.  9x more warps than one-warp-per-entity: the 1024-entity sampled
 // pool still fills all 148 SMs, and no warp walks nine dependent bags in sequence.
 template <int GW, int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)      // 64 registers: 4 CTAs (32 warps) per SM
 pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
                  const int* __restrict__ ids, long long n, float* __restrict__ out,
                  long long out_stride, int mode, float* __restrict__ bias_out, int epb) {
@@ -188,6 +188,169 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
       bias_out[e0 + threadIdx.x] = b / Ff;                           // :412
     }
     __syncthreads();
+  }
+}
+
+// ---- flat forward (mean mode, dim = 128 or 256): rows first, bags second ---------------------
+// The per-bag kernel above walks "ids -> (start,len) -> tokens -> rows" once per bag: four
+// dependent round trips for ~12 rows.  Here a CTA takes a group of entities (<= kFlatBags bags,
+// <= kFlatRows rows), resolves EVERY row address of the group in two block-wide passes (all loads
+// independent), then its 8 warps split the flat row list evenly (load balance by rows, not by
+// bags) and stream it 16 rows at a time, flushing the running sum at bag boundaries.  A bag that
+// straddles two warps' segments is finished from per-warp partial slots in fixed warp order, so
+// the result is deterministic.
+constexpr int kFlatBags = 64;
+constexpr int kFlatRows = 1024;
+constexpr int kFlatU = 16;
+
+template <int CPL>      // float4 columns per lane: dim = 128 * CPL
+__global__ void __launch_bounds__(256, 2)
+pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
+                     long long n, float* __restrict__ out, long long out_stride,
+                     float* __restrict__ bias_out, int epb) {
+  constexpr int dim = 128 * CPL;
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ arx_attr_desc s_attrs[kMaxAttr];
+  __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_off[kFlatBags + 1];
+  __shared__ int s_part_bag[8][2];
+  float* s_pool = reinterpret_cast<float*>(s_raw);                          // [kFlatBags][dim]
+  float* s_part = s_pool + (size_t)kFlatBags * dim;                         // [8][2][dim]
+  const float** s_rowptr = reinterpret_cast<const float**>(s_part + 16 * dim);   // [kFlatRows]
+  float* s_rowbias = reinterpret_cast<float*>(s_rowptr + kFlatRows);        // [kFlatRows]
+  short* s_rowbag = reinterpret_cast<short*>(s_rowbias + kFlatRows);        // [kFlatRows]
+  stage_descs(s_attrs, g_attrs, n_attr);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float Ff = (float)n_attr;
+
+  __shared__ int s_take;
+  for (long long g0 = (long long)blockIdx.x * epb; g0 < n; g0 += (long long)gridDim.x * epb) {
+   const int ng = (int)min((long long)epb, n - g0);
+   for (int first = 0; first < ng;) {                 // sub-groups that fit kFlatRows rows
+    const long long e0 = g0 + first;
+    int ne = ng - first;
+    int nb = ne * n_attr;
+    // -- pass 0: bag extents --------------------------------------------------------------
+    if (tid < nb) {
+      const int el = tid / n_attr, f = tid - el * n_attr;
+      const int e = __ldg(ids + e0 + el);
+      int s = e, L = 1;
+      if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
+      s_start[tid] = s; s_len[tid] = L;
+    }
+    if (tid < 16) { s_part_bag[tid >> 1][tid & 1] = -1; }
+    __syncthreads();
+    if (warp == 0) {                                   // exclusive scan of <= 64 lengths
+      const int a = (lane < nb) ? s_len[lane] : 0, b = (lane + 32 < nb) ? s_len[lane + 32] : 0;
+      int ia = a, ib = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int ta = __shfl_up_sync(ARX_FULL_MASK, ia, o), tb = __shfl_up_sync(ARX_FULL_MASK, ib, o);
+        if (lane >= o) { ia += ta; ib += tb; }
+      }
+      const int tot_a = __shfl_sync(ARX_FULL_MASK, ia, 31);
+      if (lane < nb) s_off[lane] = ia - a;
+      if (lane + 32 < nb) s_off[lane + 32] = tot_a + ib - b;
+      if (lane == 31) s_off[nb] = tot_a + ib;
+    }
+    __syncthreads();
+    if (tid == 0) {                                    // how many whole entities fit the row buffer
+      int k = ne;
+      while (k > 1 && s_off[k * n_attr] > kFlatRows) --k;
+      s_take = k;
+    }
+    __syncthreads();
+    ne = s_take;
+    nb = ne * n_attr;
+    first += ne;
+    const int R = s_off[nb];
+    // -- pass 1: every row address of the group (independent loads) ---------------------------
+    for (int r = tid; r < R; r += blockDim.x) {
+      int lo = 0, hi = nb;                             // bag of row r: last b with off[b] <= r
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= r) lo = mid; else hi = mid; }
+      const int f = lo % n_attr;
+      const int tok = __ldg(s_attrs[f].values + s_start[lo] + (r - s_off[lo]));
+      const Shard sh = shard_of(s_attrs[f]);
+      const bool own = owns(sh, tok);
+      const int lr = local_row(sh, tok);
+      s_rowptr[r] = own ? s_attrs[f].table + (size_t)lr * dim : nullptr;
+      s_rowbias[r] = (own && bias_out != nullptr && s_attrs[f].bias != nullptr) ? __ldg(s_attrs[f].bias + lr) : 0.f;
+      s_rowbag[r] = (short)lo;
+    }
+    __syncthreads();
+    // -- pass 2: stream the flat row list, 8 warps x equal segments ------------------------------
+    const int seg = (R + 7) >> 3;
+    const int ra = min(R, warp * seg), rb = min(R, ra + seg);
+    if (ra < rb) {
+      float4 acc[CPL];
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[c] = f4_zero();
+      int cur = s_rowbag[ra];
+      auto flush = [&](int bag) {
+        const int o = s_off[bag], e = o + s_len[bag];
+        float* dst;
+        if (o >= ra && e <= rb) dst = s_pool + (size_t)bag * dim;              // bag wholly mine
+        else {
+          const int slot = (e > rb) ? 1 : 0;                                   // continues in the next warp : started before me
+          dst = s_part + ((size_t)warp * 2 + slot) * dim;
+          if (lane == 0) s_part_bag[warp][slot] = bag;
+        }
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) { st_f4(dst + (size_t)(c * 32 + lane) * 4, acc[c]); acc[c] = f4_zero(); }
+      };
+      for (int r0 = ra; r0 < rb; r0 += kFlatU) {
+        float4 v[kFlatU][CPL];
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) {
+          const float* p = (r0 + u < rb) ? s_rowptr[r0 + u] : nullptr;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) v[u][c] = p ? ldg_f4(p + (size_t)(c * 32 + lane) * 4) : f4_zero();
+        }
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) {
+          if (r0 + u < rb) {
+            const int bag = s_rowbag[r0 + u];
+            if (bag != cur) { flush(cur); cur = bag; }
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) f4_add(acc[c], v[u][c]);
+          }
+        }
+      }
+      flush(cur);
+    }
+    __syncthreads();
+    // -- pass 3: finish the bags, mean over attributes -------------------------------------------
+    for (int i = tid; i < ne * 32 * CPL; i += blockDim.x) {
+      const int el = i / (32 * CPL), col = i - el * 32 * CPL;
+      float4 tot = f4_zero();
+      for (int f = 0; f < n_attr; ++f) {
+        const int bag = el * n_attr + f;
+        const int o = s_off[bag], L = s_len[bag];
+        const int wlo = o / seg, whi = (o + L - 1) / seg;
+        float4 s;
+        if (wlo == whi) s = ld_f4(s_pool + (size_t)bag * dim + (size_t)col * 4);
+        else {
+          s = f4_zero();
+          for (int w = wlo; w <= whi; ++w)               // fixed warp order
+            f4_add(s, ld_f4(s_part + ((size_t)w * 2 + (w < whi ? 1 : 0)) * dim + (size_t)col * 4));
+        }
+        const float Lf = (float)L;
+        tot.x += s.x / Lf; tot.y += s.y / Lf; tot.z += s.z / Lf; tot.w += s.w / Lf;     // tf.div :400
+      }
+      st_f4(out + (e0 + el) * out_stride + (size_t)col * 4,
+            make_float4(tot.x / Ff, tot.y / Ff, tot.z / Ff, tot.w / Ff));                 // reduce_mean :219,:235
+    }
+    if (bias_out != nullptr && tid < ne) {
+      float bt = 0.f;
+      for (int f = 0; f < n_attr; ++f) {
+        const int bag = tid * n_attr + f;
+        float bs = 0.f;
+        for (int r = s_off[bag]; r < s_off[bag + 1]; ++r) bs += s_rowbias[r];
+        bt += bs / (float)s_len[bag];                                                     // :404-406
+      }
+      bias_out[e0 + tid] = bt / Ff;                                                       // :412
+    }
+    __syncthreads();
+   }
   }
 }
 
@@ -616,9 +779,29 @@ inline int pick_grid(long long warps_needed, int threads) {
 
 template <int VEC>
 int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* ids, int64_t n,
-               float* out, int64_t out_stride, int mode, float* bias_out, cudaStream_t st) {
+               float* out, int64_t out_stride, int mode, float* bias_out, int max_rows, cudaStream_t st) {
   const int nvec = dim / VEC;
   const int threads = 256;
+  if (VEC == 4 && mode == ARX_POOL_MEAN && (dim == 128 || dim == 256) && max_rows > 0 && max_rows <= kFlatRows &&
+      n_attr <= kFlatBags) {
+    // flat row-list kernel (see pool_fwd_flat_kernel): groups of up to kFlatBags bags per CTA pass
+    int epb = kFlatBags / n_attr;
+    while (epb > 1 && (n + epb - 1) / epb < 2LL * arx_num_sms()) --epb;       // keep >= 2 CTAs per SM busy
+    const size_t smem = (size_t)(kFlatBags + 16) * dim * 4 + (size_t)kFlatRows * (8 + 4 + 2);
+    long long blocks = (n + epb - 1) / epb;
+    const long long cap = (long long)arx_num_sms() * 16;
+    const int grid = (int)(blocks > cap ? cap : blocks);
+    static bool cfg1 = false, cfg2 = false;
+    if (dim == 128) {
+      if (!cfg1) { cudaFuncSetAttribute(pool_fwd_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = true; }
+      pool_fwd_flat_kernel<1><<<grid, threads, smem, st>>>(attrs, n_attr, ids, (long long)n, out, (long long)out_stride, bias_out, epb);
+    } else {
+      if (!cfg2) { cudaFuncSetAttribute(pool_fwd_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg2 = true; }
+      pool_fwd_flat_kernel<2><<<grid, threads, smem, st>>>(attrs, n_attr, ids, (long long)n, out, (long long)out_stride, bias_out, epb);
+    }
+    ARX_CHECK_LAUNCH();
+    return ARX_OK;
+  }
   // entities per CTA: 4 when that still gives >= 2 CTAs per SM, fewer for small batches;
   // bounded so the staging buffer stays under the 48 KB static-opt-in-free limit.
   int epb = 4;
@@ -647,14 +830,14 @@ int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* i
 
 extern "C" int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* ent_ids,
                             int64_t n, float* out, int64_t out_stride, int mode, float* bias_out,
-                            void* stream) {
+                            int max_rows_per_entity, void* stream) {
   if (!attrs || !ent_ids || !out || n_attr < 1 || n_attr > kMaxAttr || dim < 1 || n < 0) return ARX_E_BADARG;
   if (mode != ARX_POOL_MEAN && mode != ARX_POOL_CONCAT) return ARX_E_BADARG;
   if (n == 0) return ARX_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool v4 = (dim % 4 == 0) && (out_stride % 4 == 0) && (((uintptr_t)out & 15) == 0);
-  return v4 ? launch_fwd<4>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, st)
-            : launch_fwd<1>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, st);
+  return v4 ? launch_fwd<4>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, max_rows_per_entity, st)
+            : launch_fwd<1>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, 0, st);
 }
 
 extern "C" int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const int32_t* ent_ids,

@@ -281,6 +281,39 @@ class LatentProductModel(object):
         self.batch_loss = batch_loss
         return float(loss_val.item()) if sync else loss_val
 
+    # ------------------------------------------------------------------ CUDA graph ----
+    def capture_step(self, users_dev, items_dev, loss=None):
+        """Capture one training step (fixed batch size, loss and learning rate) into a CUDA graph:
+        ~35 kernel launches replayed with one driver call.  The batch ids live in static device
+        buffers that replay_step() refills; the sampled pool and its positive mask are refreshed in
+        place by EmbeddingAttribute.pass_sampled_items().  The step given here is executed once
+        eagerly first (it sizes every cached buffer) — it is a real training step."""
+        self._g_users = users_dev.to(torch.int32).clone()
+        self._g_items = items_dev.to(torch.int32).clone()
+        self._g_loss_kind = loss
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
+        torch.cuda.current_stream().wait_stream(side)
+        n0 = _lib.launch_count
+        gs = self.global_step.eval()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._g_loss = self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
+        self._g_launches = _lib.launch_count - n0
+        _lib.launch_count = n0                       # nothing ran during capture
+        self.global_step.assign(gs)
+
+    def replay_step(self, users, items, sync=True):
+        """One captured training step on new ids (device or pinned-host int32 tensors)."""
+        self._g_users.copy_(users, non_blocking=True)
+        self._g_items.copy_(items, non_blocking=True)
+        self._graph.replay()
+        _lib.launch_count += self._g_launches
+        self.global_step.assign(self.global_step.eval() + 1)
+        return float(self._g_loss.item()) if sync else self._g_loss
+
     # ------------------------------------------------------------------ batching ------
     def get_batch(self, data, loss='ce', hist=None):
         """hmf_model.py:230-241: mb independent random.choice draws (with replacement)."""

@@ -52,6 +52,7 @@ def parse():
     ap.add_argument('--cpu-mb', type=int, default=256, help='rows per CPU-baseline step (bounded sample)')
     ap.add_argument('--cpu-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='launch every kernel eagerly instead of replaying a CUDA graph')
     return ap.parse_args()
 
 
@@ -114,7 +115,7 @@ def build_workload(a, rank, world):
     ua, ia, i2l, l2i = synthetic.make_dataset(a.n_users, a.n_items, a.n_mulhot, a.vocab_m, a.mean_len, 64,
                                               1.05, seed=0)
     n_batches = a.warmup + a.steps
-    users, items = synthetic.make_interactions(a.n_users, a.n_items, a.mb * n_batches * 2, seed=rank)
+    users, items = synthetic.make_interactions(a.n_users, a.n_items, a.mb * world * n_batches * 2, seed=rank)
     pop, counts = np.unique(items, return_counts=True)
     p = np.power(counts / counts.sum(), 0.5)
     p = p / p.sum()
@@ -203,7 +204,8 @@ def main():
                            a.dim, a.mb, a.n_users, a.n_items, a.n_mulhot, a.mean_len, a.vocab_m, a.loss,
                            (' n_sampled=%d n_resample=%d' % (a.n_sampled, a.n_resample)) if a.loss == 'mw' else '',
                            a.keep_prob),
-           'global_batch': a.mb * world, 'parallelism': 'replicas x%d' % world if world > 1 else 'single GPU',
+           'global_batch': a.mb * world, 'parallelism': ('tables row-sharded x%d (row t on rank t %% N), RS/AR/AG of pooled vectors over NCCL' % world)
+           if world > 1 else 'single GPU',
            'l2_policy': 'inputs larger than L2: tables+accumulators 3.7 GB, rows gathered at random each step'}
 
     if a.impl == 'reference':
@@ -240,32 +242,50 @@ def main():
     from arecsys_b200 import _lib
     from arecsys_b200.hmf.hmf_model import LatentProductModel
     from arecsys_b200.utils.prepare_train import DeviceItemSampler
-    ua, ia, i2l, l2i, users, items, pop, p, pos = build_workload(a, rank, world)
+    # N > 1: tables row-sharded over the ranks (row t on rank t % N), weak scaling: the global batch
+    # is N * mb interactions, identical on every rank (same seed); rank r scores rows [r*mb,(r+1)*mb)
+    ua, ia, i2l, l2i, users, items, pop, p, pos = build_workload(a, 0, world)
     n_sampled = a.n_sampled if a.loss == 'mw' else None
-    model = LatentProductModel(a.n_users, a.n_items, a.dim, 1, a.mb, a.lr, 1.0, ua, ia, i2l, l2i,
-                               loss_function=a.loss, dropout=a.keep_prob, n_sampled=n_sampled, seed=1)
+    if world > 1:
+        from arecsys_b200.hmf.sharded import ShardedLatentProductModel
+        model = ShardedLatentProductModel(a.n_users, a.n_items, a.dim, 1, a.mb, a.lr, 1.0, ua, ia, i2l, l2i,
+                                          loss_function=a.loss, dropout=a.keep_prob, n_sampled=n_sampled, seed=1)
+    else:
+        model = LatentProductModel(a.n_users, a.n_items, a.dim, 1, a.mb, a.lr, 1.0, ua, ia, i2l, l2i,
+                                   loss_function=a.loss, dropout=a.keep_prob, n_sampled=n_sampled, seed=1)
     if a.loss != 'ce':
         model.prepare_warp(pos, pos)
-    sampler = DeviceItemSampler(pop, p, dev, seed=rank)
-    mb = a.mb
+    sampler = DeviceItemSampler(pop, p, dev, seed=0)
+    mb = a.mb * world                       # rows per (global) step
     nb = a.warmup + a.steps
     u_host = torch.from_numpy(users[:2 * nb * mb].reshape(2 * nb, mb)).pin_memory()
     i_host = torch.from_numpy(items[:2 * nb * mb].reshape(2 * nb, mb)).pin_memory()
     u_dev = u_host[:nb].to(dev)
     i_dev = i_host[:nb].to(dev)
 
-    state = {'step': 0}
+    state = {'step': 0, 'graph': False}
+    use_graph = (world == 1) and not a.no_graph
 
     def run_step(u, it, sync):
         sampled = None
         if a.loss == 'mw' and state['step'] % a.n_resample == 0:
             sampled = sampler.sample(a.n_sampled)
+            if world > 1:
+                torch.distributed.broadcast(sampled, 0)       # every rank must score the same pool
         state['step'] += 1
+        if state['graph'] and _lib.timeline is None:
+            if sampled is not None:
+                model.att_emb.pass_sampled_items(sampled)      # in place: the graph reads the same buffers
+            return model.replay_step(u, it, sync=sync)
         return model.step(None, u, it, None, sampled, None, loss=a.loss, sync=sync)
 
     # ---------------- value: ids resident in HBM ---------------------------------------
     for s in range(a.warmup):
         run_step(u_dev[s], i_dev[s], False)
+    if use_graph:
+        model.capture_step(u_dev[0], i_dev[0], loss=a.loss)    # whole step -> one CUDA graph launch
+        state['graph'] = True
+        run_step(u_dev[1], i_dev[1], False)
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -308,8 +328,8 @@ def main():
     if rank != 0:
         return
     ms_step = ms_total / a.steps
-    value = world * mb * a.steps / (ms_total / 1e3)
-    e2e_v = world * mb * a.steps / (max(ms_e2e, wall_e2e) / 1e3)
+    value = mb * a.steps / (ms_total / 1e3)               # mb already counts all ranks' rows
+    e2e_v = mb * a.steps / (max(ms_e2e, wall_e2e) / 1e3)
 
     # ---------------- per-kernel durations and roofline -----------------------------------
     agg = {}
@@ -335,8 +355,9 @@ def main():
                       'frac': nbytes_unique / us / 1e3 / peak, 'traffic': None,
                       'achieved_nominal': nbytes_nominal / us / 1e3, 'algorithmic_bytes': nbytes_unique,
                       'algorithmic_bytes_nominal': nbytes_nominal, 'avg_us': us, 'kernel': what, 'peak_source': peak_src}
-    roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_kernel<32,4> user side, 4096 bags')
-    roof('arx_pool_bwd_apply:user', ub['bwd_unique'], ub['bwd_nominal'], 'pool_bwd_apply_kernel<4> user side')
+    if world == 1:       # per-rank byte counts under sharding are 1/N of these: roofline only at N=1
+        roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_kernel<32,4> user side, 4096 bags')
+        roof('arx_pool_bwd_apply:user', ub['bwd_unique'], ub['bwd_nominal'], 'pool_bwd_apply_kernel<4> user side')
     dom = max(roofs, key=lambda k: per_kernel[k]['ms_per_step']) if roofs else None
 
     out = {'metric': 'interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
@@ -345,7 +366,7 @@ def main():
            'clocks': clk,
            'e2e': {'value': e2e_v, 'unit': 'interactions/s', 'h2d_bytes_per_step': 2 * mb * 4,
                    'd2h_bytes_per_step': 4, 'ms_per_step': max(ms_e2e, wall_e2e) / a.steps, 'last_loss': last},
-           'gpu_launches': launches,
+           'gpu_launches': launches, 'launch_mode': 'cuda graph replay (1 graph launch per step)' if use_graph else 'eager',
            'roofline': roofs.get(dom), 'roofline_all': roofs, 'per_kernel': per_kernel,
            'batch_stats': {'user_occurrences': ub['occ'], 'user_unique_rows': ub['uniq'],
                            'item_occurrences': ib['occ'], 'item_unique_rows': ib['uniq']}}

@@ -61,7 +61,10 @@ typedef struct arx_attr_desc {
 int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim,
                  const int32_t* ent_ids, int64_t n,
                  float* out, int64_t out_stride, int mode,
-                 float* bias_out /* [n] or NULL */, void* stream);
+                 float* bias_out /* [n] or NULL */,
+                 int max_rows_per_entity /* upper bound of sum_f len_f over the store (static), or 0 =
+                                            unknown: enables the flat row-list kernel when <= 1024 */,
+                 void* stream);
 
 /* Integer part of K2 only (mulhot_index.py:48-67): flat token index and segment id
  * vectors for one multi-hot attribute; bit-exact parity target.  offsets[n+1] is an

@@ -295,3 +295,36 @@ def test_checkpoint_roundtrip(cuda, tmp_path):
     for k, v in before.items():
         assert torch.equal(model.att_emb.params[k], v)
     assert model.global_step.eval() == 1
+
+
+def test_cuda_graph_replay_matches_eager_steps(cuda):
+    """The captured step (bench.py's launch mode) must train exactly like the eager step."""
+    from arecsys_b200 import _lib
+    _lib.exact_fp32 = True
+    try:
+        a, om, ua, ia = _build(128, mb=32, n_sampled=12, loss='mw', keep_prob=1.0)
+        b, _, _, _ = _build(128, mb=32, n_sampled=12, loss='mw', keep_prob=1.0)
+        rng = np.random.default_rng(23)
+        users = [rng.integers(0, 60, 32).astype(np.int32) for _ in range(5)]
+        items = [rng.integers(0, 50, 32).astype(np.int32) for _ in range(5)]
+        pos = positives(np.concatenate(users), np.concatenate(items), 60, rng, n_items=50)
+        a.prepare_warp(pos, pos); b.prepare_warp(pos, pos)
+        s1 = [int(v) for v in rng.permutation(50)[:12]]; s2 = [int(v) for v in rng.permutation(50)[:12]]
+        T = lambda x: torch.tensor(x, device='cuda')
+        la = [a.step(None, users[0].tolist(), items[0].tolist(), None, s1, None, loss='mw')]
+        b.att_emb.pass_sampled_items(s1)
+        b.capture_step(T(users[0]), T(items[0]), loss='mw')          # runs step 0 eagerly, then captures
+        lb = [float(b._g_loss.item())] if False else [None]
+        for k in range(1, 5):
+            smp = s2 if k == 3 else None
+            la.append(a.step(None, users[k].tolist(), items[k].tolist(), None, smp, None, loss='mw'))
+            if smp is not None:
+                b.att_emb.pass_sampled_items(smp)
+            lb.append(b.replay_step(T(users[k]), T(items[k])))
+        for k in range(1, 5):
+            assert abs(la[k] - lb[k]) <= 1e-5 * max(1.0, abs(la[k])), (k, la, lb)
+        for k2, v in a.att_emb.params.items():
+            torch.testing.assert_close(b.att_emb.params[k2], v, rtol=1e-5, atol=1e-6)
+        assert a.global_step.eval() == b.global_step.eval() == 5
+    finally:
+        _lib.exact_fp32 = False

@@ -588,20 +588,61 @@ class EmbeddingAttribute(object):
     def apply_gradients(self, lr, opt=OPT_ADAGRAD, grad_scale=None):
         """De-duplicated sparse optimizer step on every table set with pending gradients
         (hmf_model.py:146-151; lstm/seqModel.py:173-182)."""
-        for ts in self.sets.values():
-            if not ts.pending:
-                continue
-            ready = getattr(ts, '_ready', None)
-            if ready is not None:
-                plan, arena, bias = ready
-                ts._ready = None
-            else:
-                plan = self._plan_for(ts, ts.pending)
-                arena, bias = self._arena(ts.pending)
-            _lib.tag = ts.prefix
-            call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
-                 arena.stride(0), ptr(bias), float(lr), ptr(grad_scale), opt, None, None)
+        # The table sets are independent and each of their kernels is latency-bound on its own
+        # (random 512-byte rows, L2 atomics): run them on parallel streams (parallel branches of the
+        # captured CUDA graph) so that their memory traffic overlaps.
+        main = torch.cuda.current_stream()
+        busy = [ts for ts in self.sets.values() if ts.pending]
+        forks = []
+        for k, ts in enumerate(busy):
+            side = self.side_stream(k) if (len(busy) > 1 and k > 0 and _lib.timeline is None) else None
+            if side is not None:
+                side.wait_stream(main)
+                forks.append(side)
+            with torch.cuda.stream(side if side is not None else main):
+                ready = getattr(ts, '_ready', None)
+                if ready is not None:
+                    plan, arena, bias = ready
+                    ts._ready = None
+                else:
+                    plan = self._plan_for(ts, ts.pending)
+                    arena, bias = self._arena(ts.pending)
+                _lib.tag = ts.prefix
+                call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
+                     arena.stride(0), ptr(bias), float(lr), ptr(grad_scale), opt, None, None)
             ts.pending = []
+        for side in forks:
+            main.wait_stream(side)
+
+    def side_stream(self, k):
+        if not hasattr(self, '_side_streams'):
+            self._side_streams = {}
+        if k not in self._side_streams:
+            self._side_streams[k] = torch.cuda.Stream(device=self.device)
+        return self._side_streams[k]
+
+    def pool_many(self, requests):
+        """Several independent pooling launches on parallel streams.  requests: list of
+        (prefix, ids, mode, want_bias, kwargs); outputs are allocated on the calling stream first.
+        Returns the list of pool() results."""
+        main = torch.cuda.current_stream()
+        outs = []
+        for prefix, ids, mode, want_bias, kw in requests:
+            a0, na = self.sets[prefix].attr_range(kw.get('no_id', False), kw.get('no_attribute', False))
+            width = self.dim if mode == POOL_MEAN else self.dim * na
+            outs.append((torch.empty((ids.numel(), width), dtype=torch.float32, device=self.device),
+                         torch.empty((ids.numel(),), dtype=torch.float32, device=self.device) if want_bias else None))
+        res, forks = [], []
+        for k, ((prefix, ids, mode, want_bias, kw), (o, b)) in enumerate(zip(requests, outs)):
+            side = self.side_stream(k) if (k > 0 and _lib.timeline is None) else None
+            if side is not None:
+                side.wait_stream(main)
+                forks.append(side)
+            with torch.cuda.stream(side if side is not None else main):
+                res.append(self.pool(prefix, ids, mode, want_bias, out=o, bias_out=b, **kw))
+        for side in forks:
+            main.wait_stream(side)
+        return res
 
     def row_gradients(self, prefix):
         """Oracle check: dense gradients of every table of `prefix` from the pending lookups,

@@ -119,6 +119,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_epi[4][32 * 33];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long m0 = (long long)blockIdx.y * BM, n0 = (long long)blockIdx.x * BN;
@@ -191,9 +192,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       umma_commit(smem_u32(&tmem_full_bar));           // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> (warp transpose in smem) -> coalesced global =====
+    // tcgen05.ld hands thread t the 32 consecutive columns of accumulator row t; writing those
+    // directly makes every store instruction touch 32 different rows (32 half-empty sectors).
+    // A 32x33 shared-memory transpose per warp turns each store into one 128-byte row segment.
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const long long row = m0 + q * 32 + lane;
+    float* sm = s_epi[q];
     if (num_kb > 0) {
       mbar_wait(smem_u32(&tmem_full_bar), 0);
       tc_fence_after();
@@ -207,25 +211,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = 0.f;
       }
-      if (row < p.M) {
-        float* crow = p.C + row * p.ldc;
-        const long long nb = n0 + c * 32;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const long long n = nb + i;
-          if (n < p.N) {
-            float x = p.alpha * v[i];
-            if (p.atomic_out) {
-              if (p.bias_n && blockIdx.z == 0) x += p.bias_n[n];
-              atomicAdd(crow + n, x);
-            } else {
-              if (p.bias_n) x += p.bias_n[n];
-              if (p.beta != 0.f) x += p.beta * crow[n];
-              crow[n] = x;
-            }
+      for (int i = 0; i < 32; ++i) sm[lane * 33 + i] = v[i];
+      __syncwarp();
+      const long long n = n0 + c * 32 + lane;
+      const bool nok = n < p.N;
+      const float bias = (nok && p.bias_n && (!p.atomic_out || blockIdx.z == 0)) ? p.bias_n[n] : 0.f;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        const long long row = m0 + q * 32 + rr;
+        if (row < p.M && nok) {
+          float x = p.alpha * sm[rr * 33 + lane] + bias;
+          float* dst = p.C + row * p.ldc + n;
+          if (p.atomic_out) atomicAdd(dst, x);
+          else {
+            if (p.beta != 0.f) x += p.beta * *dst;
+            *dst = x;
           }
         }
       }
+      __syncwarp();
     }
     tc_fence_before();
   }

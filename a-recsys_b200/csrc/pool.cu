@@ -201,10 +201,10 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
 // the result is deterministic.
 constexpr int kFlatBags = 64;
 constexpr int kFlatRows = 1024;
-constexpr int kFlatU = 16;
+constexpr int kFlatU = 8;
 
 template <int CPL>      // float4 columns per lane: dim = 128 * CPL
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, CPL == 1 ? 4 : 2)
 pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
                      long long n, float* __restrict__ out, long long out_stride,
                      float* __restrict__ bias_out, int epb) {
@@ -506,13 +506,17 @@ __global__ void plan_reset_kernel(const arx_attr_desc* __restrict__ g_attrs, arx
 template <int VEC>
 __device__ __forceinline__ typename V<VEC>::T
 reduce_bucket(const arx_bwd_plan& plan, int base, int cnt, const float* __restrict__ dout,
-              long long stride, int col, bool colok, int lane) {
+              long long stride, int col, bool colok, int lane, const float* __restrict__ dbias, float& gb) {
   using VT = typename V<VEC>::T;
   VT g = V<VEC>::zero();
+  float gbl = 0.f;                      // bias column: one bucket entry per lane, reduced at the end
   for (int k0 = 0; k0 < cnt; k0 += 32) {
     const int kc = min(32, cnt - k0);
     int src = 0; float w = 0.f;
-    if (lane < kc) { src = __ldg(plan.bucket_src + base + k0 + lane); w = __ldg(plan.bucket_w + base + k0 + lane); }
+    if (lane < kc) {
+      src = __ldg(plan.bucket_src + base + k0 + lane); w = __ldg(plan.bucket_w + base + k0 + lane);
+      if (dbias != nullptr) gbl = fmaf(w, __ldg(dbias + src), gbl);
+    }
     for (int kk0 = 0; kk0 < kc; kk0 += kRowsInFlight) {
       VT v[kRowsInFlight]; float wk[kRowsInFlight];
 #pragma unroll
@@ -526,16 +530,8 @@ reduce_bucket(const arx_bwd_plan& plan, int base, int cnt, const float* __restri
       for (int q = 0; q < kRowsInFlight; ++q) V<VEC>::fma(g, wk[q], v[q]);
     }
   }
+  gb = (dbias != nullptr) ? warp_sum(gbl) : 0.f;
   return g;
-}
-
-// lane-parallel bias gradient of one bucket (every lane walks its own bucket)
-__device__ __forceinline__ float bucket_bias(const arx_bwd_plan& plan, int base, int cnt,
-                                             const float* __restrict__ dbias) {
-  float gb = 0.f;
-  for (int k = 0; k < cnt; ++k)
-    gb = fmaf(__ldg(plan.bucket_w + base + k), __ldg(dbias + __ldg(plan.bucket_src + base + k)), gb);
-  return gb;
 }
 
 __device__ __forceinline__ void bias_update(const arx_attr_desc& a, int tok, float gb, float lr, int opt) {
@@ -600,7 +596,8 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
     for (int c0 = 0; c0 < nvec; c0 += 32) {
       const int col = c0 + lane;
       const bool colok = col < nvec;
-      const VT g = reduce_bucket<VEC>(plan, base, cnt, dout, dout_stride, col, colok, lane);
+      float gb_unused;
+      const VT g = reduce_bucket<VEC>(plan, base, cnt, dout, dout_stride, col, colok, lane, nullptr, gb_unused);
       if (colok) V<VEC>::st(part + (size_t)ch * dim + (size_t)col * VEC, g);
     }
     if (dbias != nullptr) {
@@ -661,14 +658,10 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
     const bool light = (u < nu) && (cnt <= kHeavy);
     int src0 = 0; float w0 = 0.f;
     if (light) { src0 = __ldg(plan.bucket_src + base); w0 = __ldg(plan.bucket_w + base); }
-    if (light) {                                 // bias column: each lane owns its row
-      float gb = 0.f;
-      if (dbias != nullptr && s_attrs[f].bias != nullptr) {
-        gb = bucket_bias(plan, base, cnt, dbias) * gs;
-        bias_update(s_attrs[f], tok, gb, lr, opt);
-      }
-      if (opt == ARX_OPT_NONE && bias_rows_out != nullptr) bias_rows_out[u] = gb;
-    }
+    // bias column: the lane that owns a row takes its first bucket entry here, the remaining
+    // entries are added by reduce_bucket below (one entry per lane, no dependent walk)
+    const bool row_bias = light && dbias != nullptr && s_attrs[f].bias != nullptr;
+    float gb_mine = row_bias ? w0 * __ldg(dbias + src0) : 0.f;
     const unsigned lightmask = __ballot_sync(ARX_FULL_MASK, light);
     for (int c0 = 0; c0 < nvec; c0 += 32) {
       const int col = c0 + lane;
@@ -698,8 +691,13 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
         }
 #pragma unroll
         for (int q = 0; q < kRowsPerStep; ++q) {
-          if (cq[q] > 1)                             // warp-uniform: remaining bucket entries
-            V<VEC>::add(g[q], reduce_bucket<VEC>(plan, bq[q] + 1, cq[q] - 1, dout, dout_stride, col, colok, lane));
+          if (cq[q] > 1) {                           // warp-uniform: remaining bucket entries
+            const bool wb = (c0 == 0) && dbias != nullptr && s_attrs[fq[q]].bias != nullptr;
+            float gbx;
+            V<VEC>::add(g[q], reduce_bucket<VEC>(plan, bq[q] + 1, cq[q] - 1, dout, dout_stride, col, colok, lane,
+                                                 wb ? dbias : nullptr, gbx));
+            if (lane == r + q) gb_mine += gbx;
+          }
         }
 #pragma unroll
         for (int q = 0; q < kRowsPerStep; ++q) {
@@ -718,6 +716,10 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
           }
         }
       }
+    }
+    if (light) {
+      if (row_bias) bias_update(s_attrs[f], tok, gb_mine * gs, lr, opt);
+      if (opt == ARX_OPT_NONE && bias_rows_out != nullptr) bias_rows_out[u] = row_bias ? gb_mine * gs : 0.f;
     }
   }
 }

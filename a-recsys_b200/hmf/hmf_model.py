@@ -197,7 +197,7 @@ class LatentProductModel(object):
         dU = D P, dP = D^T u, dbeta = column sums of D."""
         mb, N = D.shape
         dU = torch.empty_like(u)
-        _lib.gemm(D, P, dU, mb, self.size, N, 0, 0)
+        _lib.gemm(D, P, dU, mb, self.size, N, 0, 0, a_ready=True)     # gradients: tf32 truncation is enough
         dP = torch.empty_like(P)
         _lib.gemm(D, u, dP, N, self.size, mb, 1, 0)
         dbeta = torch.empty((N,), dtype=torch.float32, device=self.device)
@@ -230,13 +230,40 @@ class LatentProductModel(object):
         item_ids = m._ids(item_input)
         targets = m.item2logit_dev[item_ids.long()].contiguous()               # target_mapping :173
         train = not forward_only
-        u, ctx = self._user_tower(keep_prob, masks)
         eff = loss if loss is not None else self.loss_function
         if eff == 'mw' and forward_only:
             eff = 'warp'                                                       # loss_eval :130,:144
         scale = self._scale(mb)
 
-        if eff == 'mw':
+        if eff == 'mw' and self.nonlinear not in ['relu', 'tanh']:
+            # the three lookups of the step (users, sampled pool, target items) are independent:
+            # issue them on parallel streams, then the tiny dense part
+            pre = m._out_prefix()
+            sids = m.sampled_ids
+            (u0, _, urng), (Ps, bs, _), (Pt, bt, _) = m.pool_many([
+                ('user', m.u_indices['input'], POOL_MEAN, False, {}),
+                (pre, sids, POOL_MEAN, True, {}),
+                (pre, item_ids, POOL_MEAN, True, {})])
+            m._last_user = ('user', urng, m.u_indices['input'], POOL_MEAN)
+            u = m.dropout(u0, keep_prob, masks[0] if masks else None)          # :78 / embed :236
+            ctx = ('linear', m._last_user, keep_prob, getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None)
+            S = Ps.shape[0]
+            logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
+            _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)               # :112
+            tscore = torch.empty((mb,), dtype=torch.float32, device=self.device)
+            call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), bt.data_ptr(), mb, self.size, tscore.data_ptr())   # :115
+            batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+            if train:
+                D, dts = logits, m._last_dtarget
+                dU, dPs, dbs = self._scores_backward(D, u, Ps)
+                dPt = torch.empty_like(Pt)
+                call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
+                     dU.data_ptr(), dPt.data_ptr())
+                rng = m.sets[pre].attr_range()
+                m.push_grad(pre, rng, sids, POOL_MEAN, dPs, dbs)
+                m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)
+        elif eff == 'mw':
+            u, ctx = self._user_tower(keep_prob, masks)
             pre = m._out_prefix()
             Ps, bs, sids = m.pool_catalog('sampled')                           # :112
             S = Ps.shape[0]
@@ -255,6 +282,7 @@ class LatentProductModel(object):
                 m.push_grad(pre, rng, sids, POOL_MEAN, dPs, dbs)
                 m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)
         else:
+            u, ctx = self._user_tower(keep_prob, masks)
             logits = m.get_prediction(u)                                       # :118
             _, P, beta, cids, _, _ = m._last_pred
             out = m.compute_loss(logits, targets, eff, loss_func=self.loss_func, exp_p=self.loss_exp_p,

@@ -359,6 +359,13 @@ def main():
         roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_kernel<32,4> user side, 4096 bags')
         roof('arx_pool_bwd_apply:user', ub['bwd_unique'], ub['bwd_nominal'], 'pool_bwd_apply_kernel<4> user side')
     dom = max(roofs, key=lambda k: per_kernel[k]['ms_per_step']) if roofs else None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
+    if os.path.exists(tpath):    # dram bytes per launch from the committed ncu --set full capture
+        for k, r in roofs.items():
+            t = json.load(open(tpath)).get(r['kernel'])
+            if t:
+                r['traffic'] = t['dram_bytes_read'] + t['dram_bytes_write']
+                r['traffic_source'] = t['source']
 
     out = {'metric': 'interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,

@@ -517,26 +517,61 @@ class EmbeddingAttribute(object):
         self.sets[prefix].pending.append((a0, na, ids, mode, dout, dbias, plan_key))
 
     def _plan_for(self, ts, entries):
-        """Build (or fetch the cached) backward plan for the pending lookups of one table set."""
+        """Build (or fetch the cached / prefetched) backward plan for the pending lookups of one table set."""
         single_key = entries[0][6] if len(entries) == 1 else None
         if single_key is not None and single_key in ts.plans:
             return ts.plans[single_key]
+        specs = [(a0, na, ids, mode) for (a0, na, ids, mode, dout, dbias, key) in entries]
+        pre = getattr(ts, '_prefetched', None)
+        if pre is not None:
+            plan, sig, ev = pre
+            ts._prefetched = None
+            torch.cuda.current_stream().wait_event(ev)           # joins the side stream in any case
+            if sig == self._plan_sig(specs):
+                return plan
+        return self._build_plan(ts, specs, single_key)
+
+    @staticmethod
+    def _plan_sig(specs):
+        return [(a0, na, ids.data_ptr(), ids.numel(), mode) for (a0, na, ids, mode) in specs]
+
+    def prefetch_plans(self, requests):
+        """A backward plan depends only on the entity ids of the lookups, not on any gradient: start
+        building it at the top of the step on a side stream, so that the latency-bound plan kernels
+        overlap the forward pass.  requests: {prefix: [((a0, na), ids, mode), ...]} in the order the
+        matching push_grad() calls will come; apply_gradients() picks the plan up when the signature
+        matches and rebuilds otherwise."""
+        if _lib.timeline is not None:
+            return                                # the per-kernel timing pass runs everything serially
+        main = torch.cuda.current_stream()
+        for k, (prefix, reqs) in enumerate(requests.items()):
+            ts = self.sets[prefix]
+            specs = [(rng[0], rng[1], ids, mode) for (rng, ids, mode) in reqs]
+            side = self.side_stream(8 + k)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                plan = self._build_plan(ts, specs, None)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ts._prefetched = (plan, self._plan_sig(specs), ev)
+
+    def _build_plan(self, ts, specs, single_key):
         cap_occ = 0
-        for (a0, na, ids, mode, dout, dbias, key) in entries:
+        for (a0, na, ids, mode) in specs:
             cap_occ += int(ids.numel()) * sum(ts.max_len[a0:a0 + na])
         if single_key == 'catalog':
             ia = self.item_attributes     # exact: the catalog CSR is static
-            cap_occ = int(ids.numel()) * ts.n_cat + sum(len(v) for v in ia.full_values_tr)
+            cap_occ = int(specs[0][2].numel()) * ts.n_cat + sum(len(v) for v in ia.full_values_tr)
         cap_occ = max(cap_occ, 1)
         cap_rows = max(min(cap_occ, ts.total_vocab), 1)
         plan = _Plan(self.device, cap_rows, cap_occ, self.dim) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
         _lib.tag = ts.prefix
         call('arx_bwd_plan_begin', plan.c)
-        for (a0, na, ids, mode, dout, dbias, key) in entries:
+        for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
         call('arx_bwd_plan_alloc', ts.desc_ptr(0), plan.c)
         row = 0
-        for (a0, na, ids, mode, dout, dbias, key) in entries:
+        for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_fill', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), mode, row, plan.c)
             row += ids.numel() * (na if mode == POOL_CONCAT else 1)
         call('arx_bwd_plan_end', ts.desc_ptr(0), plan.c)
@@ -567,9 +602,33 @@ class EmbeddingAttribute(object):
             arena = rows[0] if rows[0].is_contiguous() else rows[0].contiguous()
             bias = biases[0].contiguous() if any_bias else None
         else:
-            arena = torch.cat(rows, 0)
-            bias = torch.cat(biases, 0) if any_bias else None
+            arena = self._adjacent(rows)
+            if arena is None:
+                arena = torch.cat(rows, 0)
+            bias = None
+            if any_bias:
+                bias = self._adjacent(biases)
+                if bias is None:
+                    bias = torch.cat(biases, 0)
         return arena, bias
+
+    @staticmethod
+    def _adjacent(parts):
+        """If the tensors are consecutive contiguous slices of one buffer (the caller wrote its gradients
+        straight into a shared arena), return the covering view instead of concatenating."""
+        base = getattr(parts[0], '_base', None)
+        if base is None or not base.is_contiguous() or base.dim() != parts[0].dim():
+            return None
+        p = parts[0].data_ptr()
+        if p != base.data_ptr():
+            return None
+        n = 0
+        for t in parts:
+            if getattr(t, '_base', None) is not base or not t.is_contiguous() or t.data_ptr() != p:
+                return None
+            p += t.numel() * t.element_size()
+            n += t.shape[0]
+        return base if n == base.shape[0] else base[:n]
 
     def sparse_sumsq(self, out, dense_semantics=()):
         """Add the table-gradient terms of clip_by_global_norm into out[0].  Table sets named in

@@ -192,13 +192,14 @@ class LatentProductModel(object):
             prefix, rng, ids, mode = lookup
             m.push_grad(prefix, rng, ids, mode, du0.contiguous())
 
-    def _scores_backward(self, D, u, P):
+    def _scores_backward(self, D, u, P, dP=None):
         """Adjoint of scores = u P^T + beta for D = d(loss)/d(scores) [mb, N]:
         dU = D P, dP = D^T u, dbeta = column sums of D."""
         mb, N = D.shape
         dU = torch.empty_like(u)
         _lib.gemm(D, P, dU, mb, self.size, N, 0, 0, a_ready=True)     # gradients: tf32 truncation is enough
-        dP = torch.empty_like(P)
+        if dP is None:
+            dP = torch.empty_like(P)
         _lib.gemm(D, u, dP, N, self.size, mb, 1, 0)
         dbeta = torch.empty((N,), dtype=torch.float32, device=self.device)
         call('arx_colsum', D.data_ptr(), mb, N, D.stride(0), dbeta.data_ptr())
@@ -240,6 +241,10 @@ class LatentProductModel(object):
             # issue them on parallel streams, then the tiny dense part
             pre = m._out_prefix()
             sids = m.sampled_ids
+            if train:
+                irng = m.sets[pre].attr_range()
+                m.prefetch_plans({'user': [(m.sets['user'].attr_range(), m.u_indices['input'], POOL_MEAN)],
+                                  pre: [(irng, sids, POOL_MEAN), (irng, item_ids, POOL_MEAN)]})
             (u0, _, urng), (Ps, bs, _), (Pt, bt, _) = m.pool_many([
                 ('user', m.u_indices['input'], POOL_MEAN, False, {}),
                 (pre, sids, POOL_MEAN, True, {}),
@@ -255,8 +260,9 @@ class LatentProductModel(object):
             batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
             if train:
                 D, dts = logits, m._last_dtarget
-                dU, dPs, dbs = self._scores_backward(D, u, Ps)
-                dPt = torch.empty_like(Pt)
+                arena = torch.empty((S + mb, self.size), dtype=torch.float32, device=self.device)
+                dPt = arena[S:]                   # both item-side gradients land in one arena: no concat
+                dU, dPs, dbs = self._scores_backward(D, u, Ps, dP=arena[:S])
                 call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
                      dU.data_ptr(), dPt.data_ptr())
                 rng = m.sets[pre].attr_range()

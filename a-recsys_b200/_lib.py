@@ -20,7 +20,8 @@ class AttrDesc(ctypes.Structure):
     """arx_attr_desc (include/arx_b200.h)."""
     _fields_ = [('table', vp), ('table_acc', vp), ('bias', vp), ('bias_acc', vp),
                 ('values', vp), ('starts', vp), ('lengths', vp), ('touch', vp),
-                ('vocab', ctypes.c_int64), ('kind', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('vocab', ctypes.c_int64), ('kind', ctypes.c_int32), ('reserved', ctypes.c_int32),
+                ('lengths_full', vp)]
 
 
 class BwdPlan(ctypes.Structure):

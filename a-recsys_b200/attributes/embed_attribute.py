@@ -39,7 +39,8 @@ class _TableSet(object):
         self.with_bias = with_bias
         self.names, self.bias_names = [], []
         descs = (AttrDesc * self.n_attr)()
-        feats_cat, feats_mul, starts, lengths = att_dev
+        feats_cat, feats_mul, starts, lengths = att_dev[:4]
+        lengths_full = att_dev[4] if len(att_dev) > 4 else None
         k = 0
         for kind, cnt in ((0, self.n_cat), (1, self.n_mul)):
             for i in range(cnt):
@@ -56,6 +57,8 @@ class _TableSet(object):
                 if kind == 1:
                     d.starts = starts[i].data_ptr()
                     d.lengths = lengths[i].data_ptr()
+                    if lengths_full is not None:
+                        d.lengths_full = lengths_full[i].data_ptr()
                 d.touch = owner.touch[name].data_ptr()
                 d.vocab = owner.touch[name].shape[0]            # global vocabulary (touch is global-sized)
                 assert d.vocab < (1 << 26), 'backward plan packs (attribute, row) in 32 bits: vocab < 2^26'
@@ -189,8 +192,33 @@ class EmbeddingAttribute(object):
     def _init_attributes(self, att):
         dev = self.device
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
-        return ([t(a) for a in att.features_cat], [t(a) for a in att.features_mulhot],
-                [t(a) for a in att.mulhot_starts], [t(a) for a in att.mulhot_lengths])
+        if self.shard is None:
+            return ([t(a) for a in att.features_cat], [t(a) for a in att.features_mulhot],
+                    [t(a) for a in att.mulhot_starts], [t(a) for a in att.mulhot_lengths])
+        # row-sharded tables: list, per bag, only the rows this rank owns (as local row numbers), so
+        # that a rank walks 1/G of every bag instead of skipping foreign rows ("CSR
+        # pre-partitioned by owner").  The full bag length stays the mean divisor.
+        G, r = self.shard
+        vals, sts, lens = [], [], []
+        for f in range(att.num_features_mulhot):
+            v, s, l = self._partition_bags(np.asarray(att.features_mulhot[f]), np.asarray(att.mulhot_starts[f]),
+                                           np.asarray(att.mulhot_lengths[f]), G, r)
+            vals.append(t(v)); sts.append(t(s)); lens.append(t(l))
+        return ([t(a) for a in att.features_cat], vals, sts, lens, [t(a) for a in att.mulhot_lengths])
+
+    @staticmethod
+    def _partition_bags(values, starts, lengths, G, r):
+        n1 = len(lengths)
+        L = lengths.astype(np.int64)
+        first = np.cumsum(L) - L
+        seg = np.repeat(np.arange(n1, dtype=np.int64), L)
+        tok = values[starts[:n1].astype(np.int64)[seg] + (np.arange(int(L.sum()), dtype=np.int64) - first[seg])]
+        own = (tok % G) == r
+        l_loc = np.bincount(seg[own], minlength=n1).astype(np.int32)
+        s_loc = np.full(len(starts), int(l_loc.sum()), dtype=np.int64)
+        s_loc[:n1] = np.cumsum(l_loc, dtype=np.int64) - l_loc
+        v_loc = np.concatenate([tok[own] // G, [0]]).astype(np.int32)      # trailing pad as in the reference arrays
+        return v_loc, s_loc.astype(np.int32), l_loc
 
     def _new_var(self, name, shape, gen, params):
         if params is not None and name in params:

@@ -79,7 +79,13 @@ __device__ __forceinline__ void stage_descs(arx_attr_desc* s_attrs, const arx_at
 // Kernels skip the rows they do not own; the host sums / exchanges the partial results.
 struct Shard { int G, r; };
 __device__ __forceinline__ Shard shard_of(const arx_attr_desc& a) {
-  Shard s; s.G = a.reserved >> 16; s.r = a.reserved & 0xffff; return s;
+  Shard s; s.G = a.reserved >> 16; s.r = a.reserved & 0xffff;
+  if (a.lengths_full != nullptr) s.G = 0;      // pre-partitioned CSR: every listed row is local already
+  return s;
+}
+// mean divisor of entity e's bag (the full bag length, also when only the owned rows are listed)
+__device__ __forceinline__ int full_len(const arx_attr_desc& a, int e, int L) {
+  return a.lengths_full != nullptr ? __ldg(a.lengths_full + e) : L;
 }
 __device__ __forceinline__ bool owns(const Shard& s, int tok) { return s.G <= 1 || (tok % s.G) == s.r; }
 __device__ __forceinline__ int local_row(const Shard& s, int tok) { return s.G <= 1 ? tok : tok / s.G; }
@@ -135,7 +141,7 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
       const float* __restrict__ bias = s_attrs[f].bias;
       const bool want_bias = (bias_out != nullptr) && (bias != nullptr);
       const Shard sh = shard_of(s_attrs[f]);
-      const float Lf = (float)L;
+      const float Lf = (float)(s_attrs[f].kind == 1 ? full_len(s_attrs[f], e, L) : 1);
       float bsum = 0.f;
       for (int c0 = 0; c0 < nvec; c0 += GW) {
         const int col = c0 + l;
@@ -211,7 +217,7 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
   constexpr int dim = 128 * CPL;
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ arx_attr_desc s_attrs[kMaxAttr];
-  __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_off[kFlatBags + 1];
+  __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_lenf[kFlatBags], s_off[kFlatBags + 1];
   __shared__ int s_part_bag[8][2];
   float* s_pool = reinterpret_cast<float*>(s_raw);                          // [kFlatBags][dim]
   float* s_part = s_pool + (size_t)kFlatBags * dim;                         // [8][2][dim]
@@ -233,9 +239,11 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
     if (tid < nb) {
       const int el = tid / n_attr, f = tid - el * n_attr;
       const int e = __ldg(ids + e0 + el);
-      int s = e, L = 1;
-      if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
-      s_start[tid] = s; s_len[tid] = L;
+      int s = e, L = 1, Lf = 1;
+      if (s_attrs[f].kind == 1) {
+        s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); Lf = full_len(s_attrs[f], e, L);
+      }
+      s_start[tid] = s; s_len[tid] = L; s_lenf[tid] = Lf;
     }
     if (tid < 16) { s_part_bag[tid >> 1][tid & 1] = -1; }
     __syncthreads();
@@ -327,13 +335,14 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
         const int o = s_off[bag], L = s_len[bag];
         const int wlo = o / seg, whi = (o + L - 1) / seg;
         float4 s;
-        if (wlo == whi) s = ld_f4(s_pool + (size_t)bag * dim + (size_t)col * 4);
+        if (L == 0) s = f4_zero();                       // sharded: none of the bag's rows live here
+        else if (wlo == whi) s = ld_f4(s_pool + (size_t)bag * dim + (size_t)col * 4);
         else {
           s = f4_zero();
           for (int w = wlo; w <= whi; ++w)               // fixed warp order
             f4_add(s, ld_f4(s_part + ((size_t)w * 2 + (w < whi ? 1 : 0)) * dim + (size_t)col * 4));
         }
-        const float Lf = (float)L;
+        const float Lf = (float)s_lenf[bag];
         tot.x += s.x / Lf; tot.y += s.y / Lf; tot.z += s.z / Lf; tot.w += s.w / Lf;     // tf.div :400
       }
       st_f4(out + (e0 + el) * out_stride + (size_t)col * 4,
@@ -345,7 +354,7 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
         const int bag = tid * n_attr + f;
         float bs = 0.f;
         for (int r = s_off[bag]; r < s_off[bag + 1]; ++r) bs += s_rowbias[r];
-        bt += bs / (float)s_len[bag];                                                     // :404-406
+        bt += bs / (float)s_lenf[bag];                                                    // :404-406
       }
       bias_out[e0 + tid] = bt / Ff;                                                       // :412
     }
@@ -476,10 +485,13 @@ plan_fill_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int 
     const int f = (int)(p - ei * n_attr);
     const int e = __ldg(ids + ei);
     int s = e, L = 1;
-    if (s_attrs[f].kind == 1) { s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); }
+    int Lf = 1;
+    if (s_attrs[f].kind == 1) {
+      s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); Lf = full_len(s_attrs[f], e, L);
+    }
     const int* __restrict__ values = s_attrs[f].values;
     int* touch = s_attrs[f].touch;
-    const float w = invF / (float)L;
+    const float w = invF / (float)Lf;
     const int row = (mode == ARX_POOL_MEAN) ? (int)(row_base + ei) : (int)(row_base + ei * n_attr + f);
     const Shard sh = shard_of(s_attrs[f]);
     for (int j = lane; j < L; j += 32) {

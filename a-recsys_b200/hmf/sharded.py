@@ -43,12 +43,17 @@ class ShardedLatentProductModel(LatentProductModel):
         pre = m._out_prefix()
         # ---- forward: partial pooling of owned rows, one RS + one AR --------------------------
         fwd = torch.empty((n_g, 2 * d + 1), dtype=torch.float32, device=dev)
-        pu, _, urng = m.pool('user', users_g, POOL_MEAN, False)
-        pt, bt, irng = m.pool(pre, items_g, POOL_MEAN, True)
+        irng0 = m.sets[pre].attr_range()
+        # the backward plans depend on the ids only: build them on side streams under the forward pass
+        m.prefetch_plans({'user': [(m.sets['user'].attr_range(), users_g, POOL_MEAN)],
+                          pre: [(irng0, m.sampled_ids, POOL_MEAN), (irng0, items_g, POOL_MEAN)]})
+        (pu, _, urng), (pt, bt, irng), (ps, bs, _) = m.pool_many([
+            ('user', users_g, POOL_MEAN, False, {}),
+            (pre, items_g, POOL_MEAN, True, {}),
+            (pre, m.sampled_ids, POOL_MEAN, True, {})])
         fwd[:, :d] = pu
         fwd[:, d:2 * d] = pt
         fwd[:, 2 * d] = bt
-        ps, bs, _ = m.pool(pre, m.sampled_ids, POOL_MEAN, True)
         sp = torch.cat([ps, bs[:, None]], 1)
         loc = ex.reduce_scatter_rows(fwd)
         sp = ex.all_reduce(sp)
@@ -90,3 +95,12 @@ class ShardedLatentProductModel(LatentProductModel):
             return loss_sum
         ex.all_reduce(loss_sum)
         return float(loss_sum.item())
+
+    def replay_step(self, users, items, sync=True):
+        """Captured sharded step (the NCCL exchanges are part of the graph); users / items are the
+        GLOBAL batch.  With sync the global mean loss is all-reduced and returned as a float."""
+        loss = super(ShardedLatentProductModel, self).replay_step(users, items, sync=False)
+        if not sync:
+            return loss
+        tot = self.ex.all_reduce(loss.clone())
+        return float(tot.item())

@@ -27,7 +27,7 @@ extern "C" {
 #define ARX_E_UNSUPPORTED  -3
 #define ARX_E_CAPACITY     -4
 
-#define ARX_ABI_VERSION     1
+#define ARX_ABI_VERSION     2
 #define ARX_MAX_ATTRS      64
 
 /* One attribute (= one embedding table) of one entity side.  Mirrors the per-attribute
@@ -46,7 +46,12 @@ typedef struct arx_attr_desc {
                                 left all-zero again by arx_pool_bwd_plan            */
   int64_t        vocab;
   int32_t        kind;       /* 0 = categorical, 1 = multi-hot                      */
-  int32_t        reserved;
+  int32_t        reserved;   /* row sharding: (G << 16) | rank; 0 = whole table here.  Row t of the
+                                full table lives on rank t % G at local row t / G.     */
+  const int32_t* lengths_full; /* NULL, or (kind 1, sharded) the CSR above is PRE-PARTITIONED: values
+                                holds only the rows this rank owns, already as local row numbers,
+                                starts/lengths describe those local bags (possibly empty), and
+                                lengths_full[e] is the bag's full length = the mean divisor.  */
 } arx_attr_desc;
 
 #define ARX_POOL_MEAN    0   /* out[n, dim]      = (1/F) sum_f pooled_f   (reduce_mean over attrs,

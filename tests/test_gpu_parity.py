@@ -328,3 +328,40 @@ def test_cuda_graph_replay_matches_eager_steps(cuda):
         assert a.global_step.eval() == b.global_step.eval() == 5
     finally:
         _lib.exact_fp32 = False
+
+
+@pytest.mark.parametrize('dim,G', [(8, 2), (128, 3), (128, 4)])
+def test_row_sharded_tables_on_one_device_match_unsharded(cuda, dim, G):
+    """SURVEY 8(e) on one GPU: G row-sharded copies (row t on shard t % G, pre-partitioned bags) — the sum of
+    their partial pooled vectors is the unsharded result, and their local Adagrad updates reassemble
+    to the unsharded tables."""
+    from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
+    from arecsys_b200._lib import POOL_MEAN, OPT_ADAGRAD
+    ua, ia, i2l, l2i = small_dataset(60, 50, 3, 25, 3, 7, 0, None, dim)
+    params = random_params(ua, ia, dim, 5)
+    i2l_d, l2i_d = _dicts(l2i)
+    mk = lambda shard: EmbeddingAttribute(ua, ia, 16, None, item_ind2logit_ind=i2l_d, logit_ind2item_ind=l2i_d,
+                                          params=params, shard=shard)
+    full = mk(None)
+    parts = [mk((G, r)) for r in range(G)]
+    rng = np.random.default_rng(11)
+    ids = np.concatenate([rng.integers(0, 51, 45), [50, 50, 3, 3]]).astype(np.int32)
+    dout = torch.tensor(rng.standard_normal((len(ids), dim)).astype(np.float32), device='cuda')
+    dbias = torch.tensor(rng.standard_normal(len(ids)).astype(np.float32), device='cuda')
+    ref, refb, _ = full.pool('item', full._ids(ids), POOL_MEAN, True)
+    acc, accb = torch.zeros_like(ref), torch.zeros_like(refb)
+    for m in parts:
+        o, b, _ = m.pool('item', m._ids(ids), POOL_MEAN, True)
+        acc += o; accb += b
+    np.testing.assert_allclose(acc.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(accb.cpu().numpy(), refb.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    for m in [full] + parts:
+        m.push_grad('item', m.sets['item'].attr_range(), m._ids(ids), POOL_MEAN, dout.clone(), dbias.clone())
+        m.apply_gradients(0.3, OPT_ADAGRAD)
+    for name in full.sets['item'].names + [b for b in full.sets['item'].bias_names if b]:
+        want = full.params[name].cpu().numpy()
+        got = np.empty_like(want)
+        for r, m in enumerate(parts):
+            got[r::G] = m.params[name].cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6, err_msg=name)
+        assert np.abs(want - np.asarray(params[name]).reshape(want.shape)).max() > 0    # something moved

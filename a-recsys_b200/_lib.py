@@ -53,6 +53,9 @@ SIGNATURES = {
     'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, i32, vp],
     'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
     'arx_gemm_tc': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
+    'arx_ce_workspace_floats': [i64, i64, vp],
+    'arx_ce_fwd': [vp, vp, vp, i64, i64, i64, vp, vp, vp],
+    'arx_ce_bwd': [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp],
     'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
@@ -129,7 +132,7 @@ def call(name, *args):
     return rc
 
 
-_MAY_BE_UNSUPPORTED = ('arx_gemm_tc',)
+_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd')
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 
@@ -166,3 +169,38 @@ def gemm(A, B, C, m, n, k, trans_a, trans_b, bias=None, alpha=1.0, beta=0.0, a_r
                 alpha, beta) == 0:
             return
     call('arx_gemm', A.data_ptr(), B.data_ptr(), C.data_ptr(), m, n, k, trans_a, trans_b, ptr(bias), alpha, beta)
+
+
+def ce_supported(M, N, d):
+    """Shapes the fused scoring + cross-entropy kernels take (arx_ce_fwd / arx_ce_bwd)."""
+    return (not exact_fp32) and d in (32, 64, 96, 128) and M % 4 == 0 and N % 4 == 0 and M > 0 and N > 0
+
+
+def ce_fwd(U_r, P_r, beta, M, N, d):
+    """lse[M] of logits = U P^T + beta, logits never materialised.  U_r / P_r: tf32-rounded operands."""
+    n = ctypes.c_int64(0)
+    rc = load().arx_ce_workspace_floats(M, N, ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError('arx_ce_workspace_floats failed (%d)' % rc)
+    ws = torch.empty(n.value, dtype=torch.float32, device=U_r.device)
+    lse = torch.empty(M, dtype=torch.float32, device=U_r.device)
+    if call('arx_ce_fwd', U_r.data_ptr(), P_r.data_ptr(), ptr(beta), M, N, d, ws.data_ptr(), lse.data_ptr()) != 0:
+        return None
+    return lse
+
+
+def ce_bwd(U_r, P_r, beta, lse, g, target, M, N, d, dP=None):
+    """(dU, dP, dbeta) of sum_r g[r] * (lse[r] - logits[r, target[r]])."""
+    dev = U_r.device
+    UT = torch.empty((d, M), dtype=torch.float32, device=dev)
+    PT = torch.empty((d, N), dtype=torch.float32, device=dev)
+    call('arx_transpose', U_r.data_ptr(), M, d, UT.data_ptr(), 0)
+    call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
+    dU = torch.empty((M, d), dtype=torch.float32, device=dev)
+    if dP is None:
+        dP = torch.empty((N, d), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((N,), dtype=torch.float32, device=dev)
+    if call('arx_ce_bwd', U_r.data_ptr(), P_r.data_ptr(), UT.data_ptr(), PT.data_ptr(), ptr(beta), lse.data_ptr(),
+            g.data_ptr(), target.data_ptr(), M, N, d, dU.data_ptr(), dP.data_ptr(), dbeta.data_ptr()) != 0:
+        return None
+    return dU, dP, dbeta

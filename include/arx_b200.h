@@ -159,6 +159,24 @@ int arx_gemm_tc(const float* A, const float* B, float* C, int64_t m, int64_t n, 
                 int trans_a, int trans_b, const float* bias_n, float alpha, float beta,
                 void* stream);
 
+/* K3 + K5 fused: full-catalog scoring and softmax cross-entropy without materialising the [M, N]
+ * logits (embed_attribute.py:148-206 get_prediction + :530 sparse_softmax_cross_entropy_with_logits,
+ * and tf.gradients of both, hmf_model.py:146-151).  logits[r, c] = U[r] . P[c] + beta[c]; tf32 operands
+ * (pass arx_round_tf32 copies), fp32 accumulation in TMEM.
+ *   arx_ce_fwd : lse[r] = ln sum_c exp(logits[r, c]).  workspace: arx_ce_workspace_floats() floats.
+ *                The row loss is lse[r] - logits[r, target[r]] (arx_rowdot_fwd on the gathered target rows).
+ *   arx_ce_bwd : with D[r, c] = g[r] * (exp(logits[r, c] - lse[r]) - [c == target[r]]):
+ *                dU [M, d] = D P,  dP [N, d] = D^T U,  dbeta [N] = column sums of D (or NULL).
+ *                UT [d, M] and PT [d, N] are the transposed operands (arx_transpose).
+ * d must be 32, 64, 96 or 128 and M, N multiples of 4; otherwise ARX_E_UNSUPPORTED (the caller then
+ * materialises the logits: arx_gemm_tc + arx_loss_rows). */
+int arx_ce_workspace_floats(int64_t M, int64_t N, int64_t* n_floats);
+int arx_ce_fwd(const float* U, const float* P, const float* beta, int64_t M, int64_t N, int64_t d,
+               float* workspace, float* lse, void* stream);
+int arx_ce_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
+               const float* lse, const float* g, const int32_t* target, int64_t M, int64_t N, int64_t d,
+               float* dU, float* dP, float* dbeta, void* stream);
+
 /* dst[c, r] = src[r, c] (fp32).  Stages an MN-major operand K-major for arx_gemm_tc;
  * round_tf32_out != 0 also rounds to the nearest tf32 (see arx_round_tf32). */
 int arx_transpose(const float* src, int64_t rows, int64_t cols, float* dst, int round_tf32_out,

@@ -418,7 +418,7 @@ class EmbeddingAttribute(object):
     # -- embed_attribute.py:525-649 --------------------------------------------------------
     def compute_loss(self, logits, item_target, loss='ce', true_rank=False, loss_func='log',
                      exp_p=1.005, device='/gpu:0', row_scale=None, want_grad=True, pos_rows=None,
-                     forward_only=False):
+                     forward_only=False, unmasked=False):
         """Per-row loss [mb].  With want_grad the gradient d(sum_b row_scale_b * loss_b)/d logits
         overwrites `logits` in place (the scores are not needed afterwards) and, for 'mw',
         d/d target-score is returned through self._last_dtarget."""
@@ -437,7 +437,7 @@ class EmbeddingAttribute(object):
         else:
             tgt = item_target if isinstance(item_target, torch.Tensor) else self._ids(item_target)
         pos_row = pos_ptr = pos_idx = None
-        if loss != 'ce':
+        if loss != 'ce' and not unmasked:
             key = ('mw' if loss == 'mw' else 'full') + ('_eval' if forward_only else '_train')
             pos_ptr, pos_idx = self._positives(key)
             pos_row = pos_rows if pos_rows is not None else self.u_indices['input']

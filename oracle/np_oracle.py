@@ -527,7 +527,12 @@ class OracleHMF(object):
         if loss == 'mw' and forward_only:
             eff = 'warp'                                                     # :130,:144
         mask = None
-        if eff in ('warp', 'warp_eval', 'rs', 'rs-sig', 'rs-sig2', 'bbpr', 'mw'):
+        if loss == 'mw' and forward_only:
+            # hmf_model.py:209-211 runs set_mask['mw'] only: the 'warp' mask Variable behind loss_eval
+            # (:130) is never written, so the reference's mw eval loss is WARP with NO positives masked
+            # (pinned by tests/golden/ref_hmf_mw_*.npz, produced by the reference's own code)
+            mask = np.ones((len(user_input), e.logit_size), dtype=bool)
+        elif eff in ('warp', 'warp_eval', 'rs', 'rs-sig', 'rs-sig2', 'bbpr', 'mw'):
             mask = e.build_mask(user_input, eff, forward_only, item_sampled_id2idx)
         if eff == 'mw':
             logits = e.get_prediction(u, 'sampled')                          # :112

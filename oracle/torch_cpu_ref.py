@@ -180,6 +180,8 @@ class TorchRefHMF(object):
             u = self._drop(u, keep, mk(0))
         eff = 'warp' if (self.loss == 'mw' and forward_only) else self.loss
         mask = self.build_mask(user_input, eff, forward_only) if eff != 'ce' else None
+        if self.loss == 'mw' and forward_only:       # reference quirk: the 'warp' mask is never set for mw eval
+            mask = torch.ones((len(user_input), self.V), dtype=torch.bool)
         if eff == 'mw':
             logits = self.get_prediction(u, 'sampled')
             ts = self.get_target_score(u, item_input)

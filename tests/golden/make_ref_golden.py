@@ -1,0 +1,202 @@
+#!/usr/bin/env python
+"""Generate golden vectors by running the UNMODIFIED reference sources.
+
+    python tests/golden/make_ref_golden.py            # needs /root/reference (this container only)
+
+The reference (Python 2 + TensorFlow 1.0) cannot run as published: neither interpreter nor library
+is installable offline.  Its model code however parses under Python 3, so this script imports
+`/root/reference/hmf/hmf_model.py`, `attributes/embed_attribute.py`, `attributes/mulhot_index.py`
+and `attributes/attribute.py` AS THEY LIE (nothing copied, nothing edited) on top of
+`oracle/tf1_shim/tensorflow` — a small lazy-graph re-statement of the TF-1.0 ops those files call —
+and records what the reference's own graph computes: per-step training losses, the parameters after
+the last step, the eval loss and the top-k recommendation.  The fixtures land in
+`tests/golden/ref_hmf_<case>.npz`; `tests/test_ref_golden.py` holds the oracle (CPU) and the CUDA
+path (GPU) to them.
+
+Honest scope of the pin: op ORDER and model wiring are the reference's; per-op numerics are the
+shim's reading of the TF-1.0 documentation (see the shim's docstring).
+"""
+import builtins
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get('ARX_REFERENCE', '/root/reference')
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf1_shim'))
+for sub in ('attributes', 'hmf', 'lstm', 'word2vec', 'utils'):
+    sys.path.append(os.path.join(REF, sub))
+builtins.xrange = range          # python-2 builtin used without six in places
+
+import tensorflow as tf  # noqa: E402  (the shim)
+assert 'tf1_shim' in tf.__file__
+
+import attribute as ref_attribute  # noqa: E402  /root/reference/attributes/attribute.py
+from helpers import small_dataset, random_params, positives  # noqa: E402
+
+
+def to_ref_attributes(a, dim):
+    """our Attributes (same field names) -> the reference's own container class, python lists of
+    ints exactly as utils/preprocess.py builds them."""
+    r = ref_attribute.Attributes(a.num_features_cat, [x.tolist() for x in a.features_cat],
+                                 a.num_features_mulhot, [x.tolist() for x in a.features_mulhot], None,
+                                 [x.tolist() for x in a.mulhot_starts], [x.tolist() for x in a.mulhot_lengths],
+                                 list(a._embedding_classes_list_cat), list(a._embedding_classes_list_mulhot))
+    r.set_model_size(dim)
+    if hasattr(a, 'full_cat_tr'):
+        r.set_target_prediction([x.tolist() for x in a.full_cat_tr], [x.tolist() for x in a.full_values_tr],
+                                [x.tolist() for x in a.full_segids_tr],
+                                [np.asarray(x, dtype=np.float32).reshape(-1, 1).tolist() for x in a.full_lengths_tr])
+    return r
+
+
+def pack_attributes(prefix, a, out):
+    out[prefix + 'n_cat'] = a.num_features_cat
+    out[prefix + 'n_mulhot'] = a.num_features_mulhot
+    out[prefix + 'v_cat'] = np.asarray(a._embedding_classes_list_cat, dtype=np.int64)
+    out[prefix + 'v_mulhot'] = np.asarray(a._embedding_classes_list_mulhot, dtype=np.int64)
+    for i in range(a.num_features_cat):
+        out['%scat_%d' % (prefix, i)] = a.features_cat[i]
+    for i in range(a.num_features_mulhot):
+        out['%svalues_%d' % (prefix, i)] = a.features_mulhot[i]
+        out['%sstarts_%d' % (prefix, i)] = a.mulhot_starts[i]
+        out['%slengths_%d' % (prefix, i)] = a.mulhot_lengths[i]
+
+
+class MaskQueue(object):
+    """dropout hook: draws floor(keep + U) from a seeded stream and remembers every mask in call order."""
+
+    def __init__(self, seed):
+        self.rng = np.random.default_rng(seed)
+        self.taken = []
+
+    def __call__(self, shape, keep):
+        m = np.floor(self.rng.random(shape) + keep).astype(np.float32)
+        self.taken.append(m)
+        return m
+
+
+HMF_CASES = {
+    # name: loss, nonlinear, dim, n_sampled, loss_func, exp_p
+    'ce_linear': ('ce', 'linear', 8, None, 'log', 1.005),
+    'ce_relu': ('ce', 'relu', 8, None, 'log', 1.005),
+    'warp_linear': ('warp', 'linear', 8, None, 'log', 1.005),
+    'warp_tanh': ('warp', 'tanh', 8, None, 'log', 1.005),
+    'rs_log': ('rs', 'linear', 8, None, 'log', 1.005),
+    'rs_poly2': ('rs', 'linear', 8, None, 'poly2', 1.3),
+    'rs_sig_exp': ('rs-sig', 'linear', 8, None, 'exp', 1.2),
+    'rs_sig2_square': ('rs-sig2', 'linear', 8, None, 'square', 1.005),
+    'bbpr': ('bbpr', 'linear', 20, None, 'log', 1.005),
+    'mw_linear': ('mw', 'linear', 8, 12, 'log', 1.005),
+    'mw_tanh': ('mw', 'tanh', 8, 12, 'log', 1.005),
+    'mw_dim128': ('mw', 'linear', 128, 12, 'log', 1.005),
+    'ce_dim32_logit40': ('ce', 'linear', 32, None, 'log', 1.005),
+}
+
+
+def run_hmf_case(name, n_steps=6):
+    import hmf_model as ref_hmf          # /root/reference/hmf/hmf_model.py
+    loss, nonlinear, dim, ns, loss_func, exp_p = HMF_CASES[name]
+    n_users, n_items, mb, hidden, lr, keep, topn = 60, 50, 16, 5, 0.3, 0.5, 10
+    logit_size = 40 if 'logit40' in name else None
+    ua, ia, i2l, l2i = small_dataset(n_users, n_items, 3, 25, 3, 7, 0, logit_size, dim)
+    params = random_params(ua, ia, dim, 1, mlp_hidden=hidden if nonlinear != 'linear' else None)
+    V = len(l2i)
+    l2i_d = {int(v): int(l2i[v]) for v in range(V)}
+    i2l_d = {int(l2i[v]): int(v) for v in range(V)}
+
+    tf.reset_default_graph()
+    rua, ria = to_ref_attributes(ua, dim), to_ref_attributes(ia, dim)
+    model = ref_hmf.LatentProductModel(n_users, n_items, dim, 1, mb, lr, 1.0, rua, ria, i2l_d, l2i_d,
+                                       loss_function=loss, nonlinear=None if nonlinear == 'linear' else nonlinear,
+                                       dropout=keep, n_sampled=ns, top_N_items=topn, hidden_size=hidden,
+                                       loss_func=loss_func, loss_exp_p=exp_p)
+    g = tf.get_default_graph()
+    for k, v in params.items():          # inject the weights by the reference's own variable names
+        g.by_name[k].load(v)
+    trainable = sorted(v._name for v in tf.trainable_variables())
+    assert trainable == sorted(params.keys()), (trainable, sorted(params.keys()))
+    masks = MaskQueue(99)
+    tf.set_dropout_hook(masks)
+    sess = tf.Session()
+
+    out = {'case': name, 'loss': loss, 'nonlinear': nonlinear, 'dim': dim, 'n_sampled': -1 if ns is None else ns,
+           'loss_func': loss_func, 'exp_p': exp_p, 'n_users': n_users, 'n_items': n_items, 'mb': mb,
+           'hidden': hidden, 'lr': lr, 'keep_prob': keep, 'top_n': topn, 'n_steps': n_steps,
+           'l2i': np.asarray(l2i, dtype=np.int64)}
+    pack_attributes('u_', ua, out)
+    pack_attributes('i_', ia, out)
+    for k, v in params.items():
+        out['init/' + k] = v
+    rng = np.random.default_rng(17)
+    losses = []
+    id2idx = None
+    for it in range(n_steps):
+        users = rng.integers(0, n_users, mb)
+        items = rng.integers(0, V, mb)          # targets must be catalog items
+        items = np.asarray([l2i_d[int(v)] for v in items])
+        if it == 3:
+            users[:4] = users[4]
+            items[:3] = items[5]                  # duplicates inside the batch
+        pos = positives(users, items, n_users, rng, n_items=V)
+        pos = {u: [l2i_d[v] if v in l2i_d else v for v in vs] for u, vs in pos.items()}
+        model.prepare_warp(pos, pos)
+        sampled = None
+        if ns and it % 2 == 0:
+            sampled = [l2i_d[int(v)] for v in rng.permutation(V)[:ns]]
+            id2idx = {v: k for k, v in enumerate(sampled)}
+        n_before = len(masks.taken)
+        lval = model.step(sess, [int(u) for u in users], [int(i) for i in items], None, sampled, id2idx,
+                          loss=loss)
+        losses.append(float(lval))
+        out['step%d/users' % it] = users.astype(np.int64)
+        out['step%d/items' % it] = items.astype(np.int64)
+        out['step%d/sampled' % it] = np.asarray(sampled if sampled is not None else [], dtype=np.int64)
+        pu = sorted(pos.keys())
+        out['step%d/pos_users' % it] = np.asarray(pu, dtype=np.int64)
+        out['step%d/pos_ptr' % it] = np.cumsum([0] + [len(pos[u]) for u in pu]).astype(np.int64)
+        out['step%d/pos_items' % it] = np.asarray([v for u in pu for v in pos[u]], dtype=np.int64)
+        taken = masks.taken[n_before:]
+        out['step%d/n_masks' % it] = len(taken)
+        for j, m in enumerate(taken):
+            out['step%d/mask%d' % (it, j)] = m
+    out['losses'] = np.asarray(losses, dtype=np.float64)
+    for v in tf.trainable_variables():
+        out['final/' + v._name] = v.numpy()
+    # eval loss (forward_only -> keep_prob fed as 1.0, eval positives) and recommendation
+    users = rng.integers(0, n_users, mb)
+    items = np.asarray([l2i_d[int(v)] for v in rng.integers(0, V, mb)])
+    pos = positives(users, items, n_users, rng, n_items=V)
+    model.prepare_warp(pos, pos)
+    ev = model.step(sess, [int(u) for u in users], [int(i) for i in items], None, None, id2idx,
+                    forward_only=True, loss=loss)
+    out['eval/users'] = users.astype(np.int64)
+    out['eval/items'] = items.astype(np.int64)
+    pu = sorted(pos.keys())
+    out['eval/pos_users'] = np.asarray(pu, dtype=np.int64)
+    out['eval/pos_ptr'] = np.cumsum([0] + [len(pos[u]) for u in pu]).astype(np.int64)
+    out['eval/pos_items'] = np.asarray([v for u in pu for v in pos[u]], dtype=np.int64)
+    out['eval/loss'] = float(ev)
+    rec = model.step(sess, list(range(mb)), None, forward_only=True, recommend=True)
+    out['recommend/users'] = np.arange(mb, dtype=np.int64)
+    out['recommend/indices'] = np.asarray(rec, dtype=np.int64)
+    out['global_step'] = int(model.global_step.numpy())
+    tf.set_dropout_hook(None)
+    path = os.path.join(HERE, 'ref_hmf_%s.npz' % name)
+    np.savez_compressed(path, **out)
+    print('%-18s losses %s  eval %.6f  -> %s' % (name, np.round(losses, 5).tolist(), ev, os.path.basename(path)))
+
+
+def main():
+    assert os.path.isdir(REF), 'reference sources not found at %s' % REF
+    names = sys.argv[1:] or list(HMF_CASES)
+    for n in names:
+        run_hmf_case(n)
+
+
+if __name__ == '__main__':
+    main()

@@ -30,26 +30,26 @@ def embedding_lookup(params, ids, partition_strategy='mod', name=None, validate_
     """params[ids] along axis 0 (single, unpartitioned params)."""
     if isinstance(params, (list, tuple)) and len(params) == 1:
         params = params[0]
-    ps, is_ = _shape_of(params), _shape_of(ids)
-    out = None if ps is None or is_ is None else list(is_) + list(ps[1:])
-    return _op(lambda p, i: p[i.to(_t.int64)], [params, ids], name or 'embedding_lookup', out,
-               getattr(params, 'dtype', None))
+    return _tf._lookup(params, ids, name or 'embedding_lookup', getattr(params, 'dtype', None))
 
 
 def dropout(x, keep_prob, noise_shape=None, seed=None, name=None):
     """x / keep_prob * floor(keep_prob + U[0,1)).  The 0/1 mask comes from the graph's dropout hook when
     one is installed (so a test can inject the same masks into the CUDA path), else from torch's RNG."""
+    node = None
+
     def f(a, k):
         k = float(k)
         if k == 1.0:                       # floor(1 + U) == 1: identity, no mask drawn
             return a
         g = _tf.get_default_graph()
         if g.dropout_hook is not None:
-            m = _t.from_numpy(_np.asarray(g.dropout_hook(tuple(a.shape), k), dtype=_np.float32))
+            m = _t.from_numpy(_np.asarray(g.dropout_hook(tuple(a.shape), k, node), dtype=_np.float32))
         else:
             m = _t.floor(k + _t.rand(a.shape))
         return a / k * m
-    return _op(f, [x, keep_prob], 'dropout', _shape_of(x))
+    node = _op(f, [x, keep_prob], 'dropout', _shape_of(x))
+    return node
 
 
 def sparse_softmax_cross_entropy_with_logits(_sentinel=None, labels=None, logits=None, name=None):

@@ -73,10 +73,12 @@ class MaskQueue(object):
     def __init__(self, seed):
         self.rng = np.random.default_rng(seed)
         self.taken = []
+        self.by_node = []      # (graph creation index of the dropout node, mask)
 
-    def __call__(self, shape, keep):
+    def __call__(self, shape, keep, node=None):
         m = np.floor(self.rng.random(shape) + keep).astype(np.float32)
         self.taken.append(m)
+        self.by_node.append((node.seq if node is not None else len(self.by_node), m))
         return m
 
 
@@ -191,11 +193,144 @@ def run_hmf_case(name, n_steps=6):
     print('%-18s losses %s  eval %.6f  -> %s' % (name, np.round(losses, 5).tolist(), ev, os.path.basename(path)))
 
 
+LSTM_CASES = {
+    # name: loss, use_concat, use_sep_item, withAdagrad, lr, max_gradient_norm   (lstm/run.py always passes
+    # no_user_id=False)
+    # loss 'mw' is not pinned: lstm/seqModel.py:301 never hands item_sampled to add_input, so the
+    # reference's sampled-pool Variables are never written on this path (it scores garbage there).
+    'ce_mean': ('ce', False, False, True, 0.5, 5.0),
+    'ce_concat': ('ce', True, False, True, 0.5, 5.0),
+    'ce_sep_item': ('ce', False, True, True, 0.5, 5.0),
+    'ce_concat_sep': ('ce', True, True, True, 0.5, 5.0),
+    'warp_mean': ('warp', False, False, True, 0.5, 5.0),
+    'ce_sgd_clipped': ('ce', False, False, False, 2.0, 0.5),        # norm > max_gradient_norm: clipping active
+    'ce_adagrad_clipped': ('ce', False, True, True, 0.5, 0.25),
+}
+
+
+def run_lstm_case(name, n_steps=4):
+    import seqModel as ref_seq            # /root/reference/lstm/seqModel.py
+    import embed_attribute as ref_emb     # /root/reference/attributes/embed_attribute.py
+    loss, use_concat, sep, adagrad, lr, clip = LSTM_CASES[name]
+    n_users, n_items, dim, mb, T, keep, topk = 40, 30, 8, 12, 5, 0.5, 5
+    buckets = [3, T]
+    ua, ia, _, l2i = small_dataset(n_users, n_items, 2, 15, 3, 5, 0, None, dim)
+    params = random_params(ua, ia, dim, 1, scale=0.4, item_output=sep)
+    rng = np.random.default_rng(5)
+    Fu = ua.num_features_cat + ua.num_features_mulhot
+    Fi = ia.num_features_cat + ia.num_features_mulhot
+    if use_concat:
+        params['w_input_user'] = rng.uniform(-.4, .4, (Fu * dim, dim)).astype(np.float32)
+        params['w_input_item'] = rng.uniform(-.4, .4, (Fi * dim, dim)).astype(np.float32)
+    params['lstm_w'] = rng.uniform(-.4, .4, (2 * dim, 4 * dim)).astype(np.float32)
+    params['lstm_b'] = np.zeros(4 * dim, dtype=np.float32)
+    START = n_items
+    l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+    i2l_d = {v: k for k, v in l2i_d.items()}
+    i2l_d[START] = 0                                  # lstm/run.py:276-278
+
+    tf.reset_default_graph()
+    devices = ['/cpu:0'] * 3
+    rua, ria = to_ref_attributes(ua, dim), to_ref_attributes(ia, dim)
+    emb = ref_emb.EmbeddingAttribute(rua, ria, mb, None, buckets[-1], sep, i2l_d, l2i_d, devices=devices)
+    model = ref_seq.SeqModel(buckets, dim, 1, clip, mb, lr, 0.83, emb, withAdagrad=adagrad, dropoutRate=keep,
+                             START_ID=START, loss=loss, devices=devices, use_concat=use_concat, no_user_id=False,
+                             topk_n=topk)
+    g = tf.get_default_graph()
+    tfname = {'lstm_w': 'rnn/multi_rnn_cell/cell_0/lstm_cell/weights',
+              'lstm_b': 'rnn/multi_rnn_cell/cell_0/lstm_cell/biases'}
+    for k, v in params.items():
+        g.by_name[tfname.get(k, k)].load(v)
+    back = {v: k for k, v in tfname.items()}
+    trainable = sorted(back.get(v._name, v._name) for v in tf.trainable_variables())
+    assert trainable == sorted(params.keys()), (trainable, sorted(params.keys()))
+    masks = MaskQueue(7)
+    tf.set_dropout_hook(masks)
+    sess = tf.Session()
+
+    out = {'case': name, 'loss': loss, 'use_concat': use_concat, 'sep': sep, 'adagrad': adagrad, 'dim': dim,
+           'n_users': n_users, 'n_items': n_items, 'mb': mb, 'T': T, 'buckets': np.asarray(buckets), 'lr': lr,
+           'keep_prob': keep, 'topk': topk, 'n_steps': n_steps, 'START': START, 'clip': clip,
+           'l2i': np.asarray(l2i, dtype=np.int64)}
+    pack_attributes('u_', ua, out)
+    pack_attributes('i_', ia, out)
+    for k, v in params.items():
+        out['init/' + k] = v
+
+    def batch(Tb):
+        users = rng.integers(0, n_users, mb).tolist()
+        seqs = [rng.integers(0, n_items, rng.integers(1, Tb + 1)).tolist() for _ in range(mb)]
+        inp = [[START] + s_[:-1] + [START] * (Tb - len(s_)) for s_ in seqs]
+        tgt = [s_ + [START] * (Tb - len(s_)) for s_ in seqs]
+        w = [[1.0] * len(s_) + [0.0] * (Tb - len(s_)) for s_ in seqs]
+        tm = lambda l: [[l[j][i] for j in range(mb)] for i in range(Tb)]   # noqa: E731  time-major
+        return users, tm(inp), tm(tgt), tm(w), seqs
+
+    def put(tag, users, inp, tgt, w, pos):
+        out[tag + '/users'] = np.asarray(users, dtype=np.int64)
+        out[tag + '/inputs'] = np.asarray(inp, dtype=np.int64)
+        out[tag + '/targets'] = np.asarray(tgt, dtype=np.int64)
+        out[tag + '/weights'] = np.asarray(w, dtype=np.float32)
+        pu = sorted(pos.keys())
+        out[tag + '/pos_users'] = np.asarray(pu, dtype=np.int64)
+        out[tag + '/pos_ptr'] = np.cumsum([0] + [len(pos[u]) for u in pu]).astype(np.int64)
+        out[tag + '/pos_items'] = np.asarray([v for u in pu for v in pos[u]], dtype=np.int64)
+
+    losses, norms = [], []
+    for it in range(n_steps):
+        b = 0 if it == 2 else 1
+        Tb = buckets[b]
+        users, inp, tgt, w, seqs = batch(Tb)
+        pos = {u: sorted(set(s_)) for u, s_ in zip(users, seqs)}
+        emb.prepare_warp(pos, pos)
+        masks.by_node = []
+        lval = model.step(sess, users, inp, tgt, w, b)
+        fetched = [f for f in sess.fetch_log if isinstance(f, list) and len(f) == 3][-1]   # [loss, update, norm]
+        losses.append(float(lval))
+        norms.append(float(fetched[2]))
+        order = sorted(masks.by_node, key=lambda kv: kv[0])     # graph order: in_0, out_0, in_1, out_1, ...
+        assert len(order) == 2 * Tb, len(order)
+        put('step%d' % it, users, inp, tgt, w, pos)
+        out['step%d/bucket' % it] = b
+        out['step%d/in_masks' % it] = np.stack([m for _, m in order[0::2]])
+        out['step%d/out_masks' % it] = np.stack([m for _, m in order[1::2]])
+    out['losses'] = np.asarray(losses, dtype=np.float64)
+    out['gnorms'] = np.asarray(norms, dtype=np.float64)
+    for v in tf.trainable_variables():
+        out['final/' + back.get(v._name, v._name)] = v.numpy()
+    # evaluation as lstm/run.py does it: dropout10_op, forward_only step on losses_full
+    users, inp, tgt, w, seqs = batch(T)
+    pos = {u: sorted(set(s_)) for u, s_ in zip(users, seqs)}
+    emb.prepare_warp(pos, pos)
+    sess.run(model.dropout10_op)
+    ev = model.step(sess, users, inp, tgt, w, 1, forward_only=True)
+    put('eval', users, inp, tgt, w, pos)
+    out['eval/loss'] = float(ev)
+    # per-position top-k of softmax(full logits) (seqModel.py:514-519), same feeds
+    feed = {}
+    for l in range(T):
+        feed[model.targets[l].name] = emb.target_mapping(tgt)[l]
+        feed[model.target_weights[l].name] = w[l]
+    emb.add_input(feed, users, inp, forward_only=True, recommend=True, loss=loss)
+    tk = sess.run(model.topk_indexes[1], feed)
+    out['eval/topk_indexes'] = np.asarray(tk, dtype=np.int64)      # [T, mb, topk]
+    sess.run(model.dropoutAssign_op)
+    out['global_step'] = int(model.global_step.numpy())
+    tf.set_dropout_hook(None)
+    path = os.path.join(HERE, 'ref_lstm_%s.npz' % name)
+    np.savez_compressed(path, **out)
+    print('lstm %-14s losses %s gnorm %s eval %.5f -> %s' % (name, np.round(losses, 4).tolist(),
+                                                          np.round(norms, 3).tolist(), ev, os.path.basename(path)))
+
+
 def main():
     assert os.path.isdir(REF), 'reference sources not found at %s' % REF
-    names = sys.argv[1:] or list(HMF_CASES)
+    names = sys.argv[1:] or (list(HMF_CASES) + ['lstm:' + n for n in LSTM_CASES])
     for n in names:
-        run_hmf_case(n)
+        if n.startswith('lstm:'):
+            run_lstm_case(n[5:])
+        else:
+            run_hmf_case(n)
 
 
 if __name__ == '__main__':

@@ -137,3 +137,106 @@ def test_cuda_path_reproduces_reference_run(cuda, name, exact):
         assert model.global_step.eval() == int(c.d['global_step'])
     finally:
         _lib.exact_fp32 = False
+
+
+# ------------------------------------------------------------------ LSTM (lstm/seqModel.py) ---------
+LSTM_CASES = sorted(os.path.basename(p)[len('ref_lstm_'):-4] for p in glob.glob(os.path.join(GOLD, 'ref_lstm_*.npz')))
+
+
+class SeqCase(object):
+    def __init__(self, name):
+        d = np.load(os.path.join(GOLD, 'ref_lstm_%s.npz' % name))
+        self.d = d
+        self.loss = str(d['loss'])
+        self.use_concat, self.sep, self.adagrad = bool(d['use_concat']), bool(d['sep']), bool(d['adagrad'])
+        self.dim, self.mb, self.T = int(d['dim']), int(d['mb']), int(d['T'])
+        self.buckets = [int(b) for b in d['buckets']]
+        self.lr, self.keep, self.clip = float(d['lr']), float(d['keep_prob']), float(d['clip'])
+        self.START, self.topk, self.n_steps = int(d['START']), int(d['topk']), int(d['n_steps'])
+        self.ua = _attributes(d, 'u_', self.dim)
+        self.ia = _attributes(d, 'i_', self.dim)
+        l2i = d['l2i']
+        self.ia.set_target_prediction_from_map(l2i)
+        self.l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+        self.i2l_d = {v: k for k, v in self.l2i_d.items()}
+        self.i2l_d[self.START] = 0
+        self.params = {k[len('init/'):]: d[k] for k in d.files if k.startswith('init/')}
+        self.final = {k[len('final/'):]: d[k] for k in d.files if k.startswith('final/')}
+
+    def batch(self, tag):
+        d = self.d
+        pu, ptr, it = d[tag + '/pos_users'], d[tag + '/pos_ptr'], d[tag + '/pos_items']
+        pos = {int(u): [int(v) for v in it[ptr[j]:ptr[j + 1]]] for j, u in enumerate(pu)}
+        return (d[tag + '/users'].tolist(), d[tag + '/inputs'].tolist(), d[tag + '/targets'].tolist(),
+                d[tag + '/weights'].tolist(), pos)
+
+
+def test_lstm_fixtures_present():
+    assert len(LSTM_CASES) >= 6, LSTM_CASES
+
+
+@pytest.mark.parametrize('name', LSTM_CASES)
+def test_oracle_reproduces_reference_lstm_run(name):
+    import torch
+    from oracle.torch_cpu_ref import TorchRefSeq
+    c = SeqCase(name)
+    ref = TorchRefSeq(c.ua, c.ia, {k: v.copy() for k, v in c.params.items()}, c.l2i_d, c.i2l_d, loss=c.loss,
+                      keep_prob=c.keep, learning_rate=c.lr, n_sampled=None, dtype=torch.float64, size=c.dim,
+                      use_concat=c.use_concat, no_user_id=False, max_gradient_norm=c.clip, item_output=c.sep,
+                      withAdagrad=c.adagrad)
+    for it in range(c.n_steps):
+        users, inp, tgt, w, pos = c.batch('step%d' % it)
+        ref.pos, ref.pos_eval = pos, pos
+        l = ref.step_seq(users, inp, tgt, w, masks=(c.d['step%d/in_masks' % it], c.d['step%d/out_masks' % it]))
+        want = float(c.d['losses'][it])
+        assert abs(l - want) <= 2e-5 * max(1.0, abs(want)), (name, it, l, want)
+        gn = float(c.d['gnorms'][it])
+        assert abs(ref.last_gnorm - gn) <= 1e-4 * max(1.0, gn), (name, it, ref.last_gnorm, gn)
+    for k, v in c.final.items():
+        np.testing.assert_allclose(ref.p[k].detach().numpy().reshape(v.shape), v, rtol=2e-4, atol=2e-5, err_msg=k)
+    users, inp, tgt, w, pos = c.batch('eval')
+    ref.pos, ref.pos_eval = pos, pos
+    ev = ref.step_seq(users, inp, tgt, w, forward_only=True)
+    want = float(c.d['eval/loss'])
+    assert abs(ev - want) <= 2e-5 * max(1.0, abs(want)), (ev, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('exact', [True, False])
+@pytest.mark.parametrize('name', LSTM_CASES)
+def test_cuda_path_reproduces_reference_lstm_run(cuda, name, exact):
+    import torch
+    from arecsys_b200 import _lib
+    from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
+    from arecsys_b200.lstm.seqModel import SeqModel
+    c = SeqCase(name)
+    ltol, ptol = (2e-4, 2e-3) if exact else (2e-3, 2e-2)
+    _lib.exact_fp32 = exact
+    try:
+        params = {k: v.copy() for k, v in c.params.items()}
+        emb = EmbeddingAttribute(c.ua, c.ia, c.mb, None, c.T, c.sep, c.i2l_d, c.l2i_d, params=params)
+        model = SeqModel(c.buckets, c.dim, 1, c.clip, c.mb, c.lr, 0.83, emb, withAdagrad=c.adagrad,
+                         dropoutRate=c.keep, START_ID=c.START, loss=c.loss, use_concat=c.use_concat,
+                         no_user_id=False, topk_n=c.topk, params=params)
+        for it in range(c.n_steps):
+            users, inp, tgt, w, pos = c.batch('step%d' % it)
+            emb.prepare_warp(pos, pos)
+            im = torch.tensor(c.d['step%d/in_masks' % it], device='cuda')
+            om = torch.tensor(c.d['step%d/out_masks' % it], device='cuda')
+            l = model.step(None, users, inp, tgt, w, int(c.d['step%d/bucket' % it]), masks=(im, om))
+            want = float(c.d['losses'][it])
+            assert abs(l - want) <= ltol * max(1.0, abs(want)), (name, it, l, want)
+            gn = float(c.d['gnorms'][it])
+            assert abs(float(model.last_gnorm) - gn) <= 5 * ltol * max(1.0, gn), (float(model.last_gnorm), gn)
+        dense = model.dense_params()
+        for k, v in c.final.items():
+            got = (emb.params[k] if k in emb.params else dense[k][0]).cpu().numpy()
+            err = np.abs(got.reshape(v.shape) - v).max()
+            assert err <= ptol * max(1.0, np.abs(v).max()), (k, err)
+        users, inp, tgt, w, pos = c.batch('eval')
+        emb.prepare_warp(pos, pos)
+        ev = model.step(None, users, inp, tgt, w, 1, forward_only=True)
+        want = float(c.d['eval/loss'])
+        assert abs(ev - want) <= ltol * max(1.0, abs(want)), (ev, want)
+    finally:
+        _lib.exact_fp32 = False

@@ -323,12 +323,89 @@ def run_lstm_case(name, n_steps=4):
                                                           np.round(norms, 3).tolist(), ev, os.path.basename(path)))
 
 
+CBOW_CASES = {
+    # name: loss, use_sep_item, n_input_items.  loss 'mw' is not pinned: word2vec/cbow_model.py:126 references
+    # batch_loss_test, which the 'mw' branch (:118-120) never defines -> the reference raises NameError.
+    'ce_sep_ni2': ('ce', True, 2),
+    'warp_sep_ni3': ('warp', True, 3),
+    'bbpr_shared_ni1': ('bbpr', False, 1),
+    'ce_shared_ni0': ('ce', False, 0),
+}
+
+
+def run_cbow_case(name, n_steps=4):
+    import cbow_model as ref_cbow         # /root/reference/word2vec/cbow_model.py
+    loss, sep, ni = CBOW_CASES[name]
+    dim, mb, n_users, n_items, lr, keep, topn = 8, 16, 40, 30, 0.5, 0.5, 5
+    ua, ia, _, l2i = small_dataset(n_users, n_items, 2, 15, 3, 5, 0, None, dim)
+    params = random_params(ua, ia, dim, 1, scale=0.4, item_output=sep)
+    l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+    i2l_d = {v: k for k, v in l2i_d.items()}
+    tf.reset_default_graph()
+    rua, ria = to_ref_attributes(ua, dim), to_ref_attributes(ia, dim)
+    model = ref_cbow.Model(n_users, n_items, dim, mb, lr, 1.0, rua, ria, i2l_d, l2i_d, n_input_items=ni,
+                           loss_function=loss, dropout=keep, top_N_items=topn, use_sep_item=sep, n_sampled=None)
+    g = tf.get_default_graph()
+    for k, v in params.items():
+        g.by_name[k].load(v)
+    assert sorted(v._name for v in tf.trainable_variables()) == sorted(params.keys())
+    masks = MaskQueue(11)
+    tf.set_dropout_hook(masks)
+    sess = tf.Session()
+    out = {'case': name, 'loss': loss, 'sep': sep, 'ni': ni, 'dim': dim, 'mb': mb, 'n_users': n_users,
+           'n_items': n_items, 'lr': lr, 'keep_prob': keep, 'top_n': topn, 'n_steps': n_steps,
+           'l2i': np.asarray(l2i, dtype=np.int64)}
+    pack_attributes('u_', ua, out)
+    pack_attributes('i_', ia, out)
+    for k, v in params.items():
+        out['init/' + k] = v
+    rng = np.random.default_rng(3)
+    nin = max(ni, 1)
+    losses = []
+
+    def put_pos(tag, pos):
+        pu = sorted(pos.keys())
+        out[tag + '/pos_users'] = np.asarray(pu, dtype=np.int64)
+        out[tag + '/pos_ptr'] = np.cumsum([0] + [len(pos[u]) for u in pu]).astype(np.int64)
+        out[tag + '/pos_items'] = np.asarray([v for u in pu for v in pos[u]], dtype=np.int64)
+
+    for it in range(n_steps):
+        users = rng.integers(0, n_users, mb)
+        outs = rng.integers(0, n_items, mb)
+        ins = [rng.integers(0, n_items + 1, mb) for _ in range(nin)]      # may include the PAD pseudo-item
+        pos = positives(users, outs, n_users, rng, n_items=n_items)
+        model.prepare_warp(pos, pos)
+        n0 = len(masks.taken)
+        lval = model.step(sess, users.tolist(), [x.tolist() for x in ins], outs.tolist(), None, None, loss=loss)
+        assert len(masks.taken) == n0 + 1
+        losses.append(float(lval))
+        tag = 'step%d' % it
+        out[tag + '/users'] = users.astype(np.int64)
+        out[tag + '/outputs'] = outs.astype(np.int64)
+        out[tag + '/inputs'] = np.stack(ins).astype(np.int64)
+        out[tag + '/mask'] = masks.taken[-1]
+        put_pos(tag, pos)
+    out['losses'] = np.asarray(losses, dtype=np.float64)
+    for v in tf.trainable_variables():
+        out['final/' + v._name] = v.numpy()
+    ev = model.step(sess, users.tolist(), [x.tolist() for x in ins], outs.tolist(), forward_only=True, loss=loss)
+    out['eval/loss'] = float(ev)                    # loss_test on the last training batch (same positives)
+    rec = model.step(sess, users.tolist(), [x.tolist() for x in ins], forward_only=True, recommend=True)
+    out['recommend/indices'] = np.asarray(rec, dtype=np.int64)
+    tf.set_dropout_hook(None)
+    path = os.path.join(HERE, 'ref_cbow_%s.npz' % name)
+    np.savez_compressed(path, **out)
+    print('cbow %-16s losses %s eval %.5f -> %s' % (name, np.round(losses, 4).tolist(), ev, os.path.basename(path)))
+
+
 def main():
     assert os.path.isdir(REF), 'reference sources not found at %s' % REF
-    names = sys.argv[1:] or (list(HMF_CASES) + ['lstm:' + n for n in LSTM_CASES])
+    names = sys.argv[1:] or (list(HMF_CASES) + ['lstm:' + n for n in LSTM_CASES] + ['cbow:' + n for n in CBOW_CASES])
     for n in names:
         if n.startswith('lstm:'):
             run_lstm_case(n[5:])
+        elif n.startswith('cbow:'):
+            run_cbow_case(n[5:])
         else:
             run_hmf_case(n)
 

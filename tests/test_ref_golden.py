@@ -240,3 +240,89 @@ def test_cuda_path_reproduces_reference_lstm_run(cuda, name, exact):
         assert abs(ev - want) <= ltol * max(1.0, abs(want)), (ev, want)
     finally:
         _lib.exact_fp32 = False
+
+
+# ------------------------------------------------------------------ CBOW (word2vec/cbow_model.py) ---
+CBOW_CASES = sorted(os.path.basename(p)[len('ref_cbow_'):-4] for p in glob.glob(os.path.join(GOLD, 'ref_cbow_*.npz')))
+
+
+class CbowCase(object):
+    def __init__(self, name):
+        d = np.load(os.path.join(GOLD, 'ref_cbow_%s.npz' % name))
+        self.d = d
+        self.loss, self.sep, self.ni = str(d['loss']), bool(d['sep']), int(d['ni'])
+        self.dim, self.mb, self.n_users, self.n_items = int(d['dim']), int(d['mb']), int(d['n_users']), int(d['n_items'])
+        self.lr, self.keep, self.top_n, self.n_steps = float(d['lr']), float(d['keep_prob']), int(d['top_n']), int(d['n_steps'])
+        self.ua = _attributes(d, 'u_', self.dim)
+        self.ia = _attributes(d, 'i_', self.dim)
+        l2i = d['l2i']
+        self.ia.set_target_prediction_from_map(l2i)
+        self.l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+        self.i2l_d = {v: k for k, v in self.l2i_d.items()}
+        self.params = {k[len('init/'):]: d[k] for k in d.files if k.startswith('init/')}
+        self.final = {k[len('final/'):]: d[k] for k in d.files if k.startswith('final/')}
+
+    def batch(self, it):
+        d, tag = self.d, 'step%d' % it
+        pu, ptr, pit = d[tag + '/pos_users'], d[tag + '/pos_ptr'], d[tag + '/pos_items']
+        pos = {int(u): [int(v) for v in pit[ptr[j]:ptr[j + 1]]] for j, u in enumerate(pu)}
+        return d[tag + '/users'], [x for x in d[tag + '/inputs']], d[tag + '/outputs'], d[tag + '/mask'], pos
+
+
+def test_cbow_fixtures_present():
+    assert len(CBOW_CASES) >= 4, CBOW_CASES
+
+
+@pytest.mark.parametrize('name', CBOW_CASES)
+def test_oracle_reproduces_reference_cbow_run(name):
+    import torch
+    from oracle.torch_cpu_ref import TorchRefCbow
+    c = CbowCase(name)
+    ref = TorchRefCbow(c.ua, c.ia, {k: v.copy() for k, v in c.params.items()}, c.l2i_d, c.i2l_d, loss=c.loss,
+                       keep_prob=c.keep, learning_rate=c.lr, n_sampled=None, dtype=torch.float64, size=c.dim,
+                       item_output=c.sep, ni=c.ni)
+    for it in range(c.n_steps):
+        users, ins, outs, mask, pos = c.batch(it)
+        ref.pos, ref.pos_eval = pos, pos
+        l = ref.step_cbow(users, ins, outs, mask=mask)
+        want = float(c.d['losses'][it])
+        assert abs(l - want) <= 2e-5 * max(1.0, abs(want)), (name, it, l, want)
+    for k, v in c.final.items():
+        np.testing.assert_allclose(ref.p[k].detach().numpy().reshape(v.shape), v, rtol=2e-4, atol=2e-5, err_msg=k)
+    ev = ref.step_cbow(users, ins, outs, forward_only=True)
+    want = float(c.d['eval/loss'])
+    assert abs(ev - want) <= 2e-5 * max(1.0, abs(want)), (ev, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('exact', [True, False])
+@pytest.mark.parametrize('name', CBOW_CASES)
+def test_cuda_path_reproduces_reference_cbow_run(cuda, name, exact):
+    import torch
+    from arecsys_b200 import _lib
+    from arecsys_b200.word2vec.cbow_model import Model
+    c = CbowCase(name)
+    ltol, ptol = (2e-4, 2e-3) if exact else (2e-3, 2e-2)
+    _lib.exact_fp32 = exact
+    try:
+        model = Model(c.n_users, c.n_items, c.dim, c.mb, c.lr, 1.0, c.ua, c.ia, c.i2l_d, c.l2i_d, n_input_items=c.ni,
+                      loss_function=c.loss, dropout=c.keep, top_N_items=c.top_n, use_sep_item=c.sep, n_sampled=None,
+                      params={k: v.copy() for k, v in c.params.items()})
+        for it in range(c.n_steps):
+            users, ins, outs, mask, pos = c.batch(it)
+            model.prepare_warp(pos, pos)
+            l = model.step(None, users.tolist(), [x.tolist() for x in ins], outs.tolist(), None, None, loss=c.loss,
+                           masks=[torch.tensor(mask, device='cuda')])
+            want = float(c.d['losses'][it])
+            assert abs(l - want) <= ltol * max(1.0, abs(want)), (name, it, l, want)
+        for k, v in c.final.items():
+            got = model.att_emb.params[k].cpu().numpy()
+            assert np.abs(got.reshape(v.shape) - v).max() <= ptol * max(1.0, np.abs(v).max()), k
+        ev = model.step(None, users.tolist(), [x.tolist() for x in ins], outs.tolist(), forward_only=True, loss=c.loss)
+        want = float(c.d['eval/loss'])
+        assert abs(ev - want) <= ltol * max(1.0, abs(want)), (ev, want)
+        if exact:
+            rec = model.step(None, users.tolist(), [x.tolist() for x in ins], forward_only=True, recommend=True)
+            assert np.array_equal(np.asarray(rec), c.d['recommend/indices'])
+    finally:
+        _lib.exact_fp32 = False

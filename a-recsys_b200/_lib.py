@@ -51,11 +51,13 @@ SIGNATURES = {
     'arx_pool_bwd_plan': [vp, i32, vp, i64, i32, BwdPlan, vp],
     'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
     'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, i32, vp],
+    'arx_set_tuning': [ctypes.c_char_p, i32],
     'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
     'arx_gemm_tc': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
     'arx_ce_workspace_floats': [i64, i64, vp],
     'arx_ce_fwd': [vp, vp, vp, i64, i64, i64, vp, vp, vp],
     'arx_ce_bwd': [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp],
+    'arx_ce_rowloss': [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp],
     'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
@@ -187,6 +189,20 @@ def ce_fwd(U_r, P_r, beta, M, N, d):
     if call('arx_ce_fwd', U_r.data_ptr(), P_r.data_ptr(), ptr(beta), M, N, d, ws.data_ptr(), lse.data_ptr()) != 0:
         return None
     return lse
+
+
+def round_tf32(X):
+    """tf32-nearest copy of X (any size; the fused CE kernels want rounded operands)."""
+    Y = torch.empty_like(X)
+    call('arx_round_tf32', X.data_ptr(), Y.data_ptr(), X.numel())
+    return Y
+
+
+def ce_rowloss(U_r, P_r, beta, target, lse, M, N, d):
+    loss = torch.empty(M, dtype=torch.float32, device=U_r.device)
+    call('arx_ce_rowloss', U_r.data_ptr(), P_r.data_ptr(), ptr(beta), target.data_ptr(), lse.data_ptr(), M, N, d,
+         loss.data_ptr())
+    return loss
 
 
 def ce_bwd(U_r, P_r, beta, lse, g, target, M, N, d, dP=None):

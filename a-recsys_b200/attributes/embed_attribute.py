@@ -389,6 +389,35 @@ class EmbeddingAttribute(object):
         self._last_pred = (latent, P, beta, ids, pool, output_feat)
         return logits
 
+    def fused_ce(self, latent, targets, row_scale=None, want_grad=True, pool='full', output_feat=1):
+        """get_prediction (:148-206) + compute_loss(..., 'ce') (:530) + their gradients without ever writing
+        the [rows, V] logits: arx_ce_fwd / arx_ce_rowloss / arx_ce_bwd on tf32-rounded operands.
+        Returns (loss_rows [rows], (dU, dP, dbeta) or None), or None when the shape is not supported
+        (the caller then takes the materialised path)."""
+        if output_feat not in (0, 1) or isinstance(latent, list):
+            return None
+        M, d = latent.shape[0], self.dim
+        ids = self.catalog_ids if pool == 'full' else self.sampled_ids
+        N = ids.numel()
+        if not _lib.ce_supported(M, N, d):
+            return None
+        P, beta, ids = self.pool_catalog(pool, output_feat)
+        U_r = _lib.round_tf32(latent if latent.is_contiguous() else latent.contiguous())
+        P_r = _lib.round_tf32(P)
+        lse = _lib.ce_fwd(U_r, P_r, beta, M, N, d)
+        if lse is None:
+            return None
+        tgt = targets if isinstance(targets, torch.Tensor) else self._ids(targets)
+        loss = _lib.ce_rowloss(U_r, P_r, beta, tgt, lse, M, N, d)
+        self._last_pred = (latent, P, beta, ids, pool, output_feat)
+        if not want_grad:
+            return loss, None
+        g = row_scale if row_scale is not None else torch.ones(M, dtype=torch.float32, device=self.device)
+        grads = _lib.ce_bwd(U_r, P_r, beta, lse, g, tgt, M, N, d)
+        if grads is None:
+            return None
+        return loss, grads
+
     # -- embed_attribute.py:208-220 --------------------------------------------------------
     def get_target_score(self, latent, inds, device='/gpu:0'):
         ids = self._ids(inds)

@@ -197,15 +197,21 @@ pool_fwd_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
   }
 }
 
-// ---- flat forward (mean mode, dim = 128 or 256): rows first, bags second ---------------------
+// ---- flat forward (mean mode, dim = 128 or 256): rows first, entities second --------------------
 // The per-bag kernel above walks "ids -> (start,len) -> tokens -> rows" once per bag: four
 // dependent round trips for ~12 rows.  Here a CTA takes a group of entities (<= kFlatBags bags,
 // <= kFlatRows rows), resolves EVERY row address of the group in two block-wide passes (all loads
 // independent), then its 8 warps split the flat row list evenly (load balance by rows, not by
-// bags) and stream it 16 rows at a time, flushing the running sum at bag boundaries.  A bag that
-// straddles two warps' segments is finished from per-warp partial slots in fixed warp order, so
-// the result is deterministic.
-constexpr int kFlatBags = 64;
+// bags) and stream it 8 rows at a time.  Pooling is linear, so the warp keeps ONE running sum per
+// entity: acc += w_row * row with w_row = 1 / (bag length * #attributes) (the mean over the bag,
+// :400, and the mean over attributes, :219/:235, folded into the row weight), flushed at entity
+// boundaries only (every ~100 rows, not every ~12).  The bias column rides along as w_row * bias[row].
+// An entity that straddles two warps' segments is finished from per-warp partial slots in fixed warp
+// order, so the result is deterministic.  ncu (profiles/r1_fwd_flat_*.md): the previous per-bag
+// flush + 36 IEEE divisions per output float4 made the kernel issue-bound (short-scoreboard stalls on
+// the per-row shared-memory lookups), not HBM-bound.
+constexpr int kFlatBags = 64;        // bags per CTA pass (pass-0 threads, scan width)
+constexpr int kFlatEnt = 16;         // entities per CTA pass
 constexpr int kFlatRows = 1024;
 constexpr int kFlatU = 8;
 
@@ -216,26 +222,28 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
                      float* __restrict__ bias_out, int epb) {
   constexpr int dim = 128 * CPL;
   extern __shared__ __align__(16) unsigned char s_raw[];
-  __shared__ arx_attr_desc s_attrs[kMaxAttr];
-  __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_lenf[kFlatBags], s_off[kFlatBags + 1];
-  __shared__ int s_part_bag[8][2];
-  float* s_pool = reinterpret_cast<float*>(s_raw);                          // [kFlatBags][dim]
-  float* s_part = s_pool + (size_t)kFlatBags * dim;                         // [8][2][dim]
+  __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_off[kFlatBags + 1];
+  __shared__ float s_w[kFlatBags];
+  __shared__ float s_bias[kFlatEnt], s_partb[8][2];
+  __shared__ int s_take;
+  float* s_pool = reinterpret_cast<float*>(s_raw);                          // [kFlatEnt][dim]
+  float* s_part = s_pool + (size_t)kFlatEnt * dim;                          // [8][2][dim]
   const float** s_rowptr = reinterpret_cast<const float**>(s_part + 16 * dim);   // [kFlatRows]
-  float* s_rowbias = reinterpret_cast<float*>(s_rowptr + kFlatRows);        // [kFlatRows]
-  short* s_rowbag = reinterpret_cast<short*>(s_rowbias + kFlatRows);        // [kFlatRows]
+  float* s_roww = reinterpret_cast<float*>(s_rowptr + kFlatRows);           // [kFlatRows] row weight w
+  float* s_rowwb = s_roww + kFlatRows;                                      // [kFlatRows] w * bias[row]
+  arx_attr_desc* s_attrs = reinterpret_cast<arx_attr_desc*>(s_rowwb + kFlatRows);  // [n_attr]
   stage_descs(s_attrs, g_attrs, n_attr);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float Ff = (float)n_attr;
+  const bool want_bias = bias_out != nullptr;
 
-  __shared__ int s_take;
   for (long long g0 = (long long)blockIdx.x * epb; g0 < n; g0 += (long long)gridDim.x * epb) {
    const int ng = (int)min((long long)epb, n - g0);
    for (int first = 0; first < ng;) {                 // sub-groups that fit kFlatRows rows
     const long long e0 = g0 + first;
     int ne = ng - first;
     int nb = ne * n_attr;
-    // -- pass 0: bag extents --------------------------------------------------------------
+    // -- pass 0: bag extents and row weights ------------------------------------------------------
     if (tid < nb) {
       const int el = tid / n_attr, f = tid - el * n_attr;
       const int e = __ldg(ids + e0 + el);
@@ -243,9 +251,9 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
       if (s_attrs[f].kind == 1) {
         s = __ldg(s_attrs[f].starts + e); L = __ldg(s_attrs[f].lengths + e); Lf = full_len(s_attrs[f], e, L);
       }
-      s_start[tid] = s; s_len[tid] = L; s_lenf[tid] = Lf;
+      s_start[tid] = s; s_len[tid] = L;
+      s_w[tid] = 1.0f / ((float)Lf * Ff);             // tf.div by the bag length (:400), reduce_mean over attributes (:219,:235)
     }
-    if (tid < 16) { s_part_bag[tid >> 1][tid & 1] = -1; }
     __syncthreads();
     if (warp == 0) {                                   // exclusive scan of <= 64 lengths
       const int a = (lane < nb) ? s_len[lane] : 0, b = (lane + 32 < nb) ? s_len[lane + 32] : 0;
@@ -280,9 +288,10 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
       const Shard sh = shard_of(s_attrs[f]);
       const bool own = owns(sh, tok);
       const int lr = local_row(sh, tok);
+      const float w = s_w[lo];
       s_rowptr[r] = own ? s_attrs[f].table + (size_t)lr * dim : nullptr;
-      s_rowbias[r] = (own && bias_out != nullptr && s_attrs[f].bias != nullptr) ? __ldg(s_attrs[f].bias + lr) : 0.f;
-      s_rowbag[r] = (short)lo;
+      s_roww[r] = w;
+      if (want_bias) s_rowwb[r] = (own && s_attrs[f].bias != nullptr) ? w * __ldg(s_attrs[f].bias + lr) : 0.f;
     }
     __syncthreads();
     // -- pass 2: stream the flat row list, 8 warps x equal segments ------------------------------
@@ -292,71 +301,72 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
       float4 acc[CPL];
 #pragma unroll
       for (int c = 0; c < CPL; ++c) acc[c] = f4_zero();
-      int cur = s_rowbag[ra];
-      auto flush = [&](int bag) {
-        const int o = s_off[bag], e = o + s_len[bag];
-        float* dst;
-        if (o >= ra && e <= rb) dst = s_pool + (size_t)bag * dim;              // bag wholly mine
+      float accb = 0.f;
+      int cur = 0;                                     // entity of row ra
+      while (cur + 1 < ne && s_off[(cur + 1) * n_attr] <= ra) ++cur;
+      int next = s_off[(cur + 1) * n_attr];            // first row of the next entity
+      auto flush = [&](int ent) {
+        const int o = s_off[ent * n_attr], e = s_off[(ent + 1) * n_attr];
+        float* dst; float* dstb;
+        if (o >= ra && e <= rb) { dst = s_pool + (size_t)ent * dim; dstb = s_bias + ent; }     // entity wholly mine
         else {
-          const int slot = (e > rb) ? 1 : 0;                                   // continues in the next warp : started before me
-          dst = s_part + ((size_t)warp * 2 + slot) * dim;
-          if (lane == 0) s_part_bag[warp][slot] = bag;
+          const int slot = (e > rb) ? 1 : 0;           // continues in the next warp : started before me
+          dst = s_part + ((size_t)warp * 2 + slot) * dim; dstb = &s_partb[warp][slot];
         }
 #pragma unroll
         for (int c = 0; c < CPL; ++c) { st_f4(dst + (size_t)(c * 32 + lane) * 4, acc[c]); acc[c] = f4_zero(); }
+        if (lane == 0) *dstb = accb;
+        accb = 0.f;
       };
       for (int r0 = ra; r0 < rb; r0 += kFlatU) {
+        const float* p[kFlatU];
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) p[u] = (r0 + u < rb) ? s_rowptr[r0 + u] : nullptr;
         float4 v[kFlatU][CPL];
 #pragma unroll
         for (int u = 0; u < kFlatU; ++u) {
-          const float* p = (r0 + u < rb) ? s_rowptr[r0 + u] : nullptr;
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) v[u][c] = p ? ldg_f4(p + (size_t)(c * 32 + lane) * 4) : f4_zero();
+          for (int c = 0; c < CPL; ++c) v[u][c] = p[u] ? ldg_f4(p[u] + (size_t)(c * 32 + lane) * 4) : f4_zero();
         }
+        float wv[kFlatU];
+#pragma unroll
+        for (int u = 0; u < kFlatU; ++u) wv[u] = (r0 + u < rb) ? s_roww[r0 + u] : 0.f;
 #pragma unroll
         for (int u = 0; u < kFlatU; ++u) {
           if (r0 + u < rb) {
-            const int bag = s_rowbag[r0 + u];
-            if (bag != cur) { flush(cur); cur = bag; }
+            while (r0 + u >= next) { flush(cur); ++cur; next = s_off[(cur + 1) * n_attr]; }
 #pragma unroll
-            for (int c = 0; c < CPL; ++c) f4_add(acc[c], v[u][c]);
+            for (int c = 0; c < CPL; ++c) f4_fma(acc[c], wv[u], v[u][c]);
+            if (want_bias) accb += s_rowwb[r0 + u];
           }
         }
       }
       flush(cur);
     }
     __syncthreads();
-    // -- pass 3: finish the bags, mean over attributes -------------------------------------------
+    // -- pass 3: finish the entities that straddle warps -----------------------------------------
     for (int i = tid; i < ne * 32 * CPL; i += blockDim.x) {
       const int el = i / (32 * CPL), col = i - el * 32 * CPL;
+      const int o = s_off[el * n_attr], L = s_off[(el + 1) * n_attr] - o;
       float4 tot = f4_zero();
-      for (int f = 0; f < n_attr; ++f) {
-        const int bag = el * n_attr + f;
-        const int o = s_off[bag], L = s_len[bag];
+      if (L > 0) {                                       // L == 0 (sharded): none of the entity's rows live here
         const int wlo = o / seg, whi = (o + L - 1) / seg;
-        float4 s;
-        if (L == 0) s = f4_zero();                       // sharded: none of the bag's rows live here
-        else if (wlo == whi) s = ld_f4(s_pool + (size_t)bag * dim + (size_t)col * 4);
-        else {
-          s = f4_zero();
+        if (wlo == whi) tot = ld_f4(s_pool + (size_t)el * dim + (size_t)col * 4);
+        else
           for (int w = wlo; w <= whi; ++w)               // fixed warp order
-            f4_add(s, ld_f4(s_part + ((size_t)w * 2 + (w < whi ? 1 : 0)) * dim + (size_t)col * 4));
-        }
-        const float Lf = (float)s_lenf[bag];
-        tot.x += s.x / Lf; tot.y += s.y / Lf; tot.z += s.z / Lf; tot.w += s.w / Lf;     // tf.div :400
+            f4_add(tot, ld_f4(s_part + ((size_t)w * 2 + (w < whi ? 1 : 0)) * dim + (size_t)col * 4));
       }
-      st_f4(out + (e0 + el) * out_stride + (size_t)col * 4,
-            make_float4(tot.x / Ff, tot.y / Ff, tot.z / Ff, tot.w / Ff));                 // reduce_mean :219,:235
+      st_f4(out + (e0 + el) * out_stride + (size_t)col * 4, tot);
     }
-    if (bias_out != nullptr && tid < ne) {
+    if (want_bias && tid < ne) {
+      const int o = s_off[tid * n_attr], L = s_off[(tid + 1) * n_attr] - o;
       float bt = 0.f;
-      for (int f = 0; f < n_attr; ++f) {
-        const int bag = tid * n_attr + f;
-        float bs = 0.f;
-        for (int r = s_off[bag]; r < s_off[bag + 1]; ++r) bs += s_rowbias[r];
-        bt += bs / (float)s_lenf[bag];                                                    // :404-406
+      if (L > 0) {
+        const int wlo = o / seg, whi = (o + L - 1) / seg;
+        if (wlo == whi) bt = s_bias[tid];
+        else for (int w = wlo; w <= whi; ++w) bt += s_partb[w][w < whi ? 1 : 0];
       }
-      bias_out[e0 + tid] = bt / Ff;                                                       // :412
+      bias_out[e0 + tid] = bt;                                                            // :404-412
     }
     __syncthreads();
    }
@@ -781,6 +791,9 @@ pool_bwd_sumsq_kernel(int dim, arx_bwd_plan plan, const float* __restrict__ dout
   if (lane == 0 && part != 0.f) atomicAdd(sumsq, part);
 }
 
+int g_tune_flat_epb = 0;         // arx_set_tuning("flat_epb", 0 = auto | 1..16): entities per CTA of the flat forward
+int g_tune_apply_cps = 4;        // arx_set_tuning("apply_ctas_per_sm", 1..4)
+
 inline int pick_grid(long long warps_needed, int threads) {
   const int sms = arx_num_sms();
   const int wpb = threads / 32;
@@ -798,12 +811,17 @@ int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* i
   const int threads = 256;
   if (VEC == 4 && mode == ARX_POOL_MEAN && (dim == 128 || dim == 256) && max_rows > 0 && max_rows <= kFlatRows &&
       n_attr <= kFlatBags) {
-    // flat row-list kernel (see pool_fwd_flat_kernel): groups of up to kFlatBags bags per CTA pass
-    int epb = kFlatBags / n_attr;
-    while (epb > 1 && (n + epb - 1) / epb < 2LL * arx_num_sms()) --epb;       // keep >= 2 CTAs per SM busy
-    const size_t smem = (size_t)(kFlatBags + 16) * dim * 4 + (size_t)kFlatRows * (8 + 4 + 2);
+    // flat row-list kernel (see pool_fwd_flat_kernel): groups of up to kFlatBags bags / kFlatEnt entities /
+    // kFlatRows rows per CTA pass; one balanced wave when the batch allows it
+    const int cps = (dim == 128) ? 4 : 2;                                        // resident CTAs per SM
+    const long long slots = (long long)arx_num_sms() * cps;
+    int epb = std::min(kFlatBags / n_attr, kFlatEnt);
+    const int even = (int)((n + slots - 1) / slots);                             // entities per CTA for exactly one wave
+    if (even >= 1 && even < epb) epb = even;
+    if (g_tune_flat_epb > 0 && g_tune_flat_epb < epb) epb = g_tune_flat_epb;
+    const size_t smem = (size_t)(kFlatEnt + 16) * dim * 4 + (size_t)kFlatRows * (8 + 8) + (size_t)n_attr * sizeof(arx_attr_desc);
     long long blocks = (n + epb - 1) / epb;
-    const long long cap = (long long)arx_num_sms() * 16;
+    const long long cap = slots * 4;
     const int grid = (int)(blocks > cap ? cap : blocks);
     static bool cfg1 = false, cfg2 = false;
     if (dim == 128) {
@@ -934,7 +952,7 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
   if (opt != ARX_OPT_ADAGRAD && opt != ARX_OPT_SGD && opt != ARX_OPT_NONE) return ARX_E_BADARG;
   if (opt == ARX_OPT_NONE && !rows_out) return ARX_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = arx_num_sms() * 2;   // persistent (2 CTAs/SM): warps stride over the device-side row list
+  const int grid = arx_num_sms() * g_tune_apply_cps;   // persistent (2 CTAs/SM): warps stride over the device-side row list
   const bool v4 = (dim % 4 == 0) && (dout_stride % 4 == 0) && (((uintptr_t)dout & 15) == 0);
   if (v4)
     pool_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
@@ -944,6 +962,23 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
                                                     dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
+}
+
+// Launch-shape knobs for measurement sweeps (tools/bench_pool.py); defaults are the tuned values.
+extern "C" int arx_set_tuning(const char* key, int value) {
+  if (!key) return ARX_E_BADARG;
+  const auto eq = [&](const char* k) { int i = 0; while (k[i] && key[i] == k[i]) ++i; return k[i] == 0 && key[i] == 0; };
+  if (eq("flat_epb")) {
+    if (value < 0 || value > kFlatEnt) return ARX_E_BADARG;
+    g_tune_flat_epb = value;
+    return ARX_OK;
+  }
+  if (eq("apply_ctas_per_sm")) {
+    if (value < 1 || value > 4) return ARX_E_BADARG;
+    g_tune_apply_cps = value;
+    return ARX_OK;
+  }
+  return ARX_E_BADARG;
 }
 
 extern "C" int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_plan plan, const float* dout,

@@ -295,6 +295,23 @@ __global__ void ce_finalize_kernel(const float* __restrict__ part_m, const float
   lse[r] = (m + log2f(l)) / kLog2e;
 }
 
+// loss[r] = lse[r] - (U[r] . P[target[r]] + beta[target[r]]): one warp per row, same tf32-rounded operands
+// as the tensor-core pass (products of tf32 values are exact in fp32, so only the summation order differs)
+__global__ void ce_rowloss_kernel(const float* __restrict__ U, const float* __restrict__ P,
+                                  const float* __restrict__ beta, const int* __restrict__ target,
+                                  const float* __restrict__ lse, long long M, long long N, int d,
+                                  float* __restrict__ loss) {
+  const int lane = threadIdx.x & 31;
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= M) return;
+  const int t = __ldg(target + r);
+  float s = 0.f;
+  if (t >= 0 && t < N)
+    for (int c = lane; c < d; c += 32) s = fmaf(__ldg(U + r * d + c), __ldg(P + (long long)t * d + c), s);
+  s = warp_sum(s);
+  if (lane == 0) loss[r] = lse[r] - (s + ((beta != nullptr && t >= 0 && t < N) ? __ldg(beta + t) : 0.f));
+}
+
 size_t ce_smem_bytes(int mode, int d) {
   const size_t KB = d / 32;
   size_t b = KB * CE_BM * 128 + 2 * KB * CE_BN * 128;
@@ -357,6 +374,16 @@ extern "C" int arx_ce_fwd(const float* U, const float* P, const float* beta, int
   int rc = ce_launch<CE_FWD>(mr, ms, ms, p, dim3((unsigned)row_tiles, (unsigned)nsplit), st);
   if (rc != ARX_OK) return rc;
   ce_finalize_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(p.part_m, p.part_l, nsplit, M, lse);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+extern "C" int arx_ce_rowloss(const float* U, const float* P, const float* beta, const int32_t* target,
+                              const float* lse, int64_t M, int64_t N, int64_t d, float* loss, void* stream) {
+  if (!U || !P || !target || !lse || !loss || M < 0 || N <= 0 || d <= 0) return ARX_E_BADARG;
+  if (M == 0) return ARX_OK;
+  ce_rowloss_kernel<<<(unsigned)((M + 7) / 8), 256, 0, (cudaStream_t)stream>>>(U, P, beta, target, lse, (long long)M,
+                                                                             (long long)N, (int)d, loss);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

@@ -293,17 +293,26 @@ class LatentProductModel(object):
                 m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)
         else:
             u, ctx = self._user_tower(keep_prob, masks)
-            logits = m.get_prediction(u)                                       # :118
-            _, P, beta, cids, _, _ = m._last_pred
-            out = m.compute_loss(logits, targets, eff, loss_func=self.loss_func, exp_p=self.loss_exp_p,
-                                 row_scale=scale, want_grad=train, forward_only=forward_only,
-                                 unmasked=unmasked)
-            if eff == 'warp_eval':
-                return [out[0].cpu().numpy(), out[1].cpu().numpy()]            # :203-204,:220-221
-            batch_loss = out
+            fused = m.fused_ce(u, targets, scale, train) if eff == 'ce' else None
+            if fused is not None:
+                # full-catalog scoring fused with the softmax CE on the tensor cores: the [mb, V]
+                # logits (16 GB at C2) are never written (:118 + embed_attribute.py:530)
+                batch_loss, grads = fused
+                _, P, beta, cids, _, _ = m._last_pred
+                if train:
+                    dU, dP, dbeta = grads
+            else:
+                logits = m.get_prediction(u)                                   # :118
+                _, P, beta, cids, _, _ = m._last_pred
+                out = m.compute_loss(logits, targets, eff, loss_func=self.loss_func, exp_p=self.loss_exp_p,
+                                     row_scale=scale, want_grad=train, forward_only=forward_only,
+                                     unmasked=unmasked)
+                if eff == 'warp_eval':
+                    return [out[0].cpu().numpy(), out[1].cpu().numpy()]        # :203-204,:220-221
+                batch_loss = out
+                if train:
+                    dU, dP, dbeta = self._scores_backward(logits, u, P)
             if train:
-                D = logits
-                dU, dP, dbeta = self._scores_backward(D, u, P)
                 pre = m._out_prefix()
                 m.push_grad(pre, m.sets[pre].attr_range(), cids, POOL_MEAN, dP, dbeta, plan_key='catalog')
 

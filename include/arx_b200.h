@@ -173,6 +173,9 @@ int arx_gemm_tc(const float* A, const float* B, float* C, int64_t m, int64_t n, 
 int arx_ce_workspace_floats(int64_t M, int64_t N, int64_t* n_floats);
 int arx_ce_fwd(const float* U, const float* P, const float* beta, int64_t M, int64_t N, int64_t d,
                float* workspace, float* lse, void* stream);
+/* loss[r] = lse[r] - (U[r] . P[target[r]] + beta[target[r]])  (embed_attribute.py:530 on the fused path). */
+int arx_ce_rowloss(const float* U, const float* P, const float* beta, const int32_t* target, const float* lse,
+                   int64_t M, int64_t N, int64_t d, float* loss, void* stream);
 int arx_ce_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                const float* lse, const float* g, const int32_t* target, int64_t M, int64_t N, int64_t d,
                float* dU, float* dP, float* dbeta, void* stream);
@@ -264,6 +267,11 @@ int arx_dense_update(float* w, float* acc, const float* g, int64_t n, float lr,
  * (tf.nn.dropout, embed_attribute.py:236): y = x * mask / keep. */
 int arx_scale_mask(const float* x, const float* mask, float scale, int64_t n, float* y,
                    void* stream);
+
+/* Launch-shape knobs for measurement sweeps (tools/bench_pool.py): "flat_epb" = 0 (auto) | 1..16 (entities per CTA
+ * pass of the flat forward kernel), "apply_ctas_per_sm" = 1..4 (persistent grid of pool_bwd_apply).  No reference
+ * counterpart; results are identical for every setting. */
+int arx_set_tuning(const char* key, int value);
 
 int arx_abi_version(void);
 const char* arx_build_info(void);

@@ -51,6 +51,7 @@ SIGNATURES = {
     'arx_pool_bwd_plan': [vp, i32, vp, i64, i32, BwdPlan, vp],
     'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
     'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, i32, vp],
+    'arx_rows_sumsq': [vp, vp, BwdPlan, i32, vp, vp],
     'arx_set_tuning': [ctypes.c_char_p, i32],
     'arx_gemm': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],
     'arx_gemm_tc': [vp, vp, vp, i64, i64, i64, i32, i32, vp, f32, f32, vp],

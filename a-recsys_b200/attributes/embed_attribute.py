@@ -698,8 +698,24 @@ class EmbeddingAttribute(object):
             plan = self._plan_for(ts, ts.pending)
             arena, bias = self._arena(ts.pending)
             ts._ready = (plan, arena, bias)
-            call('arx_pool_bwd_sumsq', ts.desc_ptr(0), self.dim, plan.c, arena.data_ptr(), arena.stride(0),
-                 ptr(bias), out.data_ptr(), 1 if ts.prefix in dense_semantics else 0)
+            if ts.prefix in dense_semantics:
+                # merged rows through the same segment-reduce as the update (ARX_OPT_NONE), then their norm
+                rows = self._norm_scratch(ts, plan.cap_rows)
+                brow = rows[1] if bias is not None else None
+                call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
+                     arena.stride(0), ptr(bias), 0.0, None, OPT_NONE, rows[0].data_ptr(), ptr(brow))
+                call('arx_rows_sumsq', rows[0].data_ptr(), ptr(brow), plan.c, self.dim, out.data_ptr())
+            else:
+                call('arx_pool_bwd_sumsq', ts.desc_ptr(0), self.dim, plan.c, arena.data_ptr(), arena.stride(0),
+                     ptr(bias), out.data_ptr(), 0)
+
+    def _norm_scratch(self, ts, cap_rows):
+        sc = getattr(ts, '_norm_rows', None)
+        if sc is None or sc[0].shape[0] < cap_rows:
+            sc = (torch.empty((cap_rows, self.dim), dtype=torch.float32, device=self.device),
+                  torch.empty((cap_rows,), dtype=torch.float32, device=self.device))
+            ts._norm_rows = sc
+        return sc
 
     def apply_gradients(self, lr, opt=OPT_ADAGRAD, grad_scale=None):
         """De-duplicated sparse optimizer step on every table set with pending gradients

@@ -746,49 +746,62 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
   }
 }
 
-// IndexedSlices part of the global norm: sum over occurrences of w^2 * ||dOut[src]||^2.
+// IndexedSlices part of the global norm: sum over occurrences of w^2 * ||dOut[src]||^2
+// (tf.global_norm takes the norm of IndexedSlices.values: duplicates are NOT summed first).
+// Flat over the occurrence list (bucket arrays are dense in [0, counters[1])): one warp per
+// occurrence, four occurrences in flight; no per-row serial walk (hot rows hold 10^4+ entries).
 __global__ void __launch_bounds__(256)
 pool_bwd_sumsq_kernel(int dim, arx_bwd_plan plan, const float* __restrict__ dout,
-                      long long dout_stride, const float* __restrict__ dbias,
-                      const arx_attr_desc* __restrict__ g_attrs, float* __restrict__ sumsq, int merged) {
+                      long long dout_stride, const float* __restrict__ dbias, float* __restrict__ sumsq) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
+  if (plan.counters[2] != 0) return;
+  const long long nocc = min((long long)plan.counters[1], (long long)plan.cap_occ);
   float part = 0.f;
-  for (long long u = warp0; u < nu; u += nwarps) {
-    const int f = plan.uniq_attr[u];
-    const int base = plan.row_base[u];
-    const int cnt = plan.row_cnt[u];
-    const bool has_bias = dbias != nullptr && (g_attrs == nullptr || g_attrs[f].bias != nullptr);
-    if (merged) {            // dense-gradient semantics: duplicates are summed BEFORE the norm
-      for (int c = lane; c < dim; c += 32) {
-        float g = 0.f;
-        for (int k = 0; k < cnt; ++k)
-          g = fmaf(plan.bucket_w[base + k], __ldg(dout + (size_t)plan.bucket_src[base + k] * dout_stride + c), g);
-        part = fmaf(g, g, part);
+  for (long long i0 = warp0 * 32; i0 < nocc; i0 += nwarps * 32) {
+    const long long i = i0 + lane;
+    int src = 0; float w = 0.f;
+    if (i < nocc) { src = __ldg(plan.bucket_src + i); w = __ldg(plan.bucket_w + i); }
+    if (dbias != nullptr && i < nocc) { const float b = w * __ldg(dbias + src); part = fmaf(b, b, part); }
+    const int cnt = (int)min(32ll, nocc - i0);
+    for (int k0 = 0; k0 < cnt; k0 += 4) {
+      float v[4]; float wk[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int sk = __shfl_sync(ARX_FULL_MASK, src, (k0 + q) & 31);
+        wk[q] = (k0 + q < cnt) ? __shfl_sync(ARX_FULL_MASK, w, (k0 + q) & 31) : 0.f;
+        float s = 0.f;
+        for (int c = lane; c < dim; c += 32) { const float x = __ldg(dout + (size_t)sk * dout_stride + c); s = fmaf(x, x, s); }
+        v[q] = s;
       }
-      if (has_bias && lane == 0) {
-        float gb = 0.f;
-        for (int k = 0; k < cnt; ++k) gb = fmaf(plan.bucket_w[base + k], dbias[plan.bucket_src[base + k]], gb);
-        part = fmaf(gb, gb, part);
-      }
-      continue;
-    }
-    for (int k = 0; k < cnt; ++k) {
-      const int src = plan.bucket_src[base + k];
-      const float w = plan.bucket_w[base + k];
-      float s = 0.f;
-      for (int c = lane; c < dim; c += 32) {
-        const float v = w * __ldg(dout + (size_t)src * dout_stride + c);
-        s = fmaf(v, v, s);
-      }
-      if (has_bias && lane == 0) { const float b = w * dbias[src]; s = fmaf(b, b, s); }
-      part += s;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) part = fmaf(wk[q] * wk[q], v[q], part);
     }
   }
   part = warp_sum(part);
   if (lane == 0 && part != 0.f) atomicAdd(sumsq, part);
+}
+
+// Dense-gradient part of the global norm: ||merged row gradients||^2 over the rows arx_pool_bwd_apply
+// wrote with ARX_OPT_NONE (duplicates summed BEFORE the norm), plus the merged bias gradients.
+__global__ void __launch_bounds__(256)
+rows_sumsq_kernel(const float* __restrict__ rows, const float* __restrict__ brows, arx_bwd_plan plan, int dim,
+                  float* __restrict__ sumsq) {
+  const long long nu = min((long long)plan.counters[0], (long long)plan.cap_rows);
+  const long long n = nu * dim;
+  float part = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = __ldg(rows + i);
+    part = fmaf(x, x, part);
+  }
+  if (brows != nullptr)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += (long long)gridDim.x * blockDim.x) {
+      const float x = __ldg(brows + i);
+      part = fmaf(x, x, part);
+    }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0 && part != 0.f) atomicAdd(sumsq, part);
 }
 
 int g_tune_flat_epb = 0;         // arx_set_tuning("flat_epb", 0 = auto | 1..16): entities per CTA of the flat forward
@@ -985,8 +998,18 @@ extern "C" int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_p
                                   int64_t dout_stride, const float* dbias, float* sumsq, int merged,
                                   void* stream) {
   if (!dout || !sumsq || dim < 1 || !plan_args_ok(plan)) return ARX_E_BADARG;
+  if (merged) return ARX_E_UNSUPPORTED;     // dense semantics: arx_pool_bwd_apply(ARX_OPT_NONE) + arx_rows_sumsq
+  (void)attrs;
   pool_bwd_sumsq_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(
-      dim, plan, dout, (long long)dout_stride, dbias, attrs, sumsq, merged);
+      dim, plan, dout, (long long)dout_stride, dbias, sumsq);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+extern "C" int arx_rows_sumsq(const float* rows, const float* bias_rows, arx_bwd_plan plan, int dim, float* sumsq,
+                              void* stream) {
+  if (!rows || !sumsq || dim < 1 || !plan_args_ok(plan)) return ARX_E_BADARG;
+  rows_sumsq_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(rows, bias_rows, plan, dim, sumsq);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

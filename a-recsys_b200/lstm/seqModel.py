@@ -216,6 +216,17 @@ class SeqModel(object):
             eff = 'warp'                                                      # losses_full (:311,:510)
         pre = m._out_prefix()
         pool = 'sampled' if eff == 'mw' else 'full'
+        fused = m.fused_ce(Hf, tgt, row_scale, train, pool, self.output_feat) if eff == 'ce' else None
+        if fused is not None:
+            # all T*mb positions scored against the catalog and reduced to the softmax CE on the tensor
+            # cores without materialising [T*mb, V] logits (seqModel.py:480-493 + sequence_loss)
+            bl, grads = fused
+            _, P, beta, cids, _, _ = m._last_pred
+            total = (bl * row_scale).sum()
+            if not train:
+                return float(total.item()) if sync else total
+            dH, dP, dbeta = grads
+            return self._finish_step(m, pre, cids, dP, dbeta, dH, ictx, users, item_ids, T, mb, total, sync)
         P, beta, cids = m.pool_catalog(pool, self.output_feat)
         N = P.shape[0]
         users_rep = users.repeat(T) if eff != 'ce' else None
@@ -253,13 +264,19 @@ class SeqModel(object):
         if not train:
             return float(total.item()) if sync else total
 
-        rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
-        m.push_grad(pre, rng_out, cids, POOL_MEAN, dP, dbeta, plan_key=None)
         if eff == 'mw':
             dPt = torch.empty_like(Pt)
             call('arx_rowdot_bwd', Hf.data_ptr(), Pt.data_ptr(), dts_all.data_ptr(), T * mb, self.size,
                  dH.data_ptr(), dPt.data_ptr())
             m.push_grad(pre, m.sets[pre].attr_range(), tgt_items, POOL_MEAN, dPt, dts_all)
+        return self._finish_step(m, pre, cids, dP, dbeta, dH, ictx, users, item_ids, T, mb, total, sync)
+
+    def _finish_step(self, m, pre, cids, dP, dbeta, dH, ictx, users, item_ids, T, mb, total, sync):
+        """Backward through the catalog pooling, the LSTM and the input embeddings, then the clipped
+        optimizer step (seqModel.py:173-182)."""
+        dev = self.device
+        rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
+        m.push_grad(pre, rng_out, cids, POOL_MEAN, dP, dbeta, plan_key=None)
         dX = self.cell.backward(dH.view(T, mb, self.size))
         self._inputs_backward(ictx, dX, users, item_ids, T, mb)
 

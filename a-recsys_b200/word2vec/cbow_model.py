@@ -102,6 +102,7 @@ class Model(object):
         train = not forward_only
         scale = self._scale(mb)
         pre = m._out_prefix()
+        fused = None
         if eff == 'mw':
             Ps, bs, sids = m.pool_catalog('sampled', self.output_feat)
             S = Ps.shape[0]
@@ -112,20 +113,27 @@ class Model(object):
             batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
             P = Ps
         else:
-            logits = m.get_prediction(h, output_feat=self.output_feat)
+            fused = m.fused_ce(h, targets, scale, train, 'full', self.output_feat) if eff == 'ce' else None
+            if fused is not None:        # scoring + softmax CE + adjoints on the tensor cores, no [mb, V] logits
+                batch_loss, fgrads = fused
+            else:
+                logits = m.get_prediction(h, output_feat=self.output_feat)
+                batch_loss = m.compute_loss(logits, targets, eff, row_scale=scale, want_grad=train,
+                                            forward_only=forward_only)
             P, sids = m._last_pred[1], m._last_pred[3]
-            batch_loss = m.compute_loss(logits, targets, eff, row_scale=scale, want_grad=train,
-                                        forward_only=forward_only)
         loss_val = batch_loss.mean()
         if train:
-            D = logits
-            N = D.shape[1]
-            dH = torch.empty_like(h)
-            _lib.gemm(D, P, dH, mb, self.size, N, 0, 0)
-            dP = torch.empty_like(P)
-            _lib.gemm(D, h, dP, N, self.size, mb, 1, 0)
-            db = torch.empty((N,), dtype=torch.float32, device=self.device)
-            call('arx_colsum', D.data_ptr(), mb, N, D.stride(0), db.data_ptr())
+            if fused is not None:
+                dH, dP, db = fgrads
+            else:
+                D = logits
+                N = D.shape[1]
+                dH = torch.empty_like(h)
+                _lib.gemm(D, P, dH, mb, self.size, N, 0, 0)
+                dP = torch.empty_like(P)
+                _lib.gemm(D, h, dP, N, self.size, mb, 1, 0)
+                db = torch.empty((N,), dtype=torch.float32, device=self.device)
+                call('arx_colsum', D.data_ptr(), mb, N, D.stride(0), db.data_ptr())
             rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
             m.push_grad(pre, rng_out, sids, POOL_MEAN, dP, db, plan_key='catalog' if eff != 'mw' else None)
             if eff == 'mw':

@@ -138,10 +138,15 @@ int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int dim,
 /* Squared-norm term of tf.clip_by_global_norm (lstm/seqModel.py:180), accumulated into *sumsq
  * (device).  merged = 0: IndexedSlices semantics, sum over OCCURRENCES of ||w * dOut[row]||^2
  * (tables reached only through lookups; TF does not merge duplicate slices for the norm).
- * merged = 1: dense-gradient semantics, sum over unique rows of ||sum_k w_k dOut[row_k]||^2
- * (tables that also feed the scoring matmul get a dense gradient in TF). */
+ * merged = 1 (dense-gradient semantics: tables that also feed the scoring matmul get ONE dense gradient in
+ * TF, duplicates summed before the norm) returns ARX_E_UNSUPPORTED here: write the merged rows with
+ * arx_pool_bwd_apply(ARX_OPT_NONE, rows_out, bias_rows_out) and reduce them with arx_rows_sumsq. */
 int arx_pool_bwd_sumsq(const arx_attr_desc* attrs, int dim, arx_bwd_plan plan, const float* dout,
                        int64_t dout_stride, const float* dbias, float* sumsq, int merged, void* stream);
+/* *sumsq += sum of squares of rows[0 .. n_unique) x dim (+ bias_rows[0 .. n_unique) unless NULL), n_unique read
+ * from the plan on the device. */
+int arx_rows_sumsq(const float* rows, const float* bias_rows, arx_bwd_plan plan, int dim, float* sumsq,
+                   void* stream);
 
 /* K3/K4 dense contraction  C[m,n] = alpha * A[m,k] * op(B) + bias  (fp32 in/out).
  * trans_b = 1: B is [n,k] (scores = U * P^T, embed_attribute.py:171,188 after the

@@ -61,12 +61,12 @@ def test_lstm_layer_forward_backward(cuda, T, mb, d_in, H, keep, exact):
     close(out, out_r, 'out'); close(dX, Xr.grad, 'dX'); close(layer.dW, Wr.grad, 'dW'); close(layer.db, br.grad, 'db')
 
 
-def _seq_setup(loss, use_concat, no_user_id, sep=False, dim=8, mb=12, T=5, ns=None, keep=0.5, seed=0):
+def _seq_setup(loss, use_concat, no_user_id, sep=False, dim=8, mb=12, T=5, ns=None, keep=0.5, seed=0, n_items=30):
     import arecsys_b200  # noqa: F401
     from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
     from arecsys_b200.lstm.seqModel import SeqModel
     from oracle.torch_cpu_ref import TorchRefSeq
-    n_users, n_items = 40, 30
+    n_users = 40
     ua, ia, _, l2i = small_dataset(n_users, n_items, 2, 15, 3, 5, seed, None, dim)
     params = random_params(ua, ia, dim, seed + 1, scale=0.4, item_output=sep)
     rng = np.random.default_rng(seed + 5)
@@ -154,3 +154,39 @@ def test_seqmodel_recommend_and_batching(cuda):
     res = model.step_recommend(None, [3, 4], [[1, 7], [2, 8], [3, 9], [4, 1], [START, 2]], [3, 4], 1)
     assert len(res) == 2 and res[0][0] == 3 and res[0][1].shape == (5,) and res[0][2].shape == (5,)
     assert (np.diff(res[0][1]) <= 1e-7).all() and 0 < res[0][1].sum() <= 1.0 + 1e-5      # sorted probabilities
+
+
+@pytest.mark.parametrize('use_concat,sep', [(False, False), (True, True)])
+def test_seqmodel_ce_fused_tensor_core_path(cuda, use_concat, sep):
+    """loss=ce with shapes the fused kernels take (T*mb and V multiples of 4, dim 32): all positions are scored
+    and reduced by arx_ce_fwd / arx_ce_bwd without materialising [T*mb, V] logits; clip norm through the
+    merged-row path (arx_pool_bwd_apply OPT_NONE + arx_rows_sumsq)."""
+    from arecsys_b200 import _lib
+    model, ref, emb, rng, (n_users, n_items, START, dim, mb, T) = _seq_setup('ce', use_concat, False, sep, dim=32,
+                                                                             n_items=36)
+    assert _lib.ce_supported(T * mb, n_items, dim)
+    calls = []
+    orig = _lib.ce_fwd
+    _lib.ce_fwd = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        for it in range(3):
+            users, inp, out, w, seqs = _batch(rng, n_users, n_items, START, mb, T)
+            im = np.floor(rng.random((T, mb, dim)) + 0.5).astype(np.float32)
+            om = np.floor(rng.random((T, mb, dim)) + 0.5).astype(np.float32)
+            lg = model.step(None, users, inp, out, w, 1, masks=(torch.tensor(im, device='cuda'), torch.tensor(om, device='cuda')))
+            lr_ = ref.step_seq(users, inp, out, w, masks=(im, om))
+            assert abs(lg - lr_) <= 2e-3 * max(1.0, abs(lr_)), (it, lg, lr_)
+            assert abs(float(model.last_gnorm) - ref.last_gnorm) <= 1e-2 * max(1.0, ref.last_gnorm)
+            dense = model.dense_params()
+            for k, v in ref.p.items():
+                got = (emb.params[k] if k in emb.params else dense[k][0]).cpu().numpy()
+                want = v.detach().numpy()
+                err = np.abs(got.reshape(want.shape) - want).max()
+                assert err <= 2e-2 * max(1.0, np.abs(want).max()), (k, it, err)
+        users, inp, out, w, seqs = _batch(rng, n_users, n_items, START, mb, T)
+        eg = model.step(None, users, inp, out, w, 1, forward_only=True)
+        er = ref.step_seq(users, inp, out, w, forward_only=True)
+        assert abs(eg - er) <= 2e-3 * max(1.0, abs(er))
+    finally:
+        _lib.ce_fwd = orig
+    assert len(calls) == 4, 'the fused CE path did not run'

@@ -59,6 +59,10 @@ ce_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUt
   __shared__ __align__(8) uint64_t r_full, sx_full[2], sx_empty[2], s_full[2], s_empty[2], d_full, d_empty,
       b2_full[2], b2_empty[2], acc_full;
   __shared__ uint32_t tmem_base_s;
+  // per-column terms of the current S tile, staged once per tile by the epilogue warps (double-buffered):
+  // FWD / BWD_U: [0] = beta[c] * log2(e) (-inf past the catalog); BWD_P: [0] = lse[c] * log2(e), [1] = g[c]
+  __shared__ __align__(16) float s_cm[2][2][CE_BN];
+  __shared__ __align__(16) int s_ct[2][CE_BN];                      // BWD_P: target[c]
 
   const int KB = p.d >> 5;                                        // 32-wide k blocks of GEMM1
   const uint32_t r_slab = CE_BM * 128, s_slab = CE_BN * 128;      // [rows x 128 B] slabs
@@ -183,9 +187,25 @@ ce_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUt
     }
     if (MODE == CE_BWD_P) row_beta = guarded(p.beta, row, N, 0.f);
 
+    const float row_beta2 = row_beta * kLog2e;
     for (int j = 0; j < nt; ++j) {
       const int s = j & 1;
       const long long c0 = (t0 + j) * CE_BN;                        // first streamed row (= S column) of the tile
+      {   // stage the per-column terms while the MMA of this tile runs (the loads were one LDG per element before)
+        const int ci = rt & (CE_BN - 1);
+        const long long c = c0 + ci;
+        if (MODE == CE_BWD_P) {
+          if (rt < CE_BN) {
+            s_cm[s][0][ci] = (c < M) ? __ldg(p.lse + c) * kLog2e : 0.f;
+            s_cm[s][1][ci] = (c < M) ? __ldg(p.g + c) : 0.f;         // g = 0 zeroes the columns past the batch
+          } else {
+            s_ct[s][ci] = (c < M) ? __ldg(p.tgt + c) : -1;
+          }
+        } else if (rt < CE_BN) {
+          s_cm[s][0][ci] = (c < N) ? (p.beta != nullptr ? __ldg(p.beta + c) * kLog2e : 0.f) : -INFINITY;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
       mbar_wait(smem_u32(&s_full[s]), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       float v[CE_BN];
@@ -197,11 +217,11 @@ ce_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUt
       if (MODE == CE_FWD) {
         float mx = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < CE_BN; ++i) {
-          const long long c = c0 + i;
-          const float b = guarded(p.beta, c, N, 0.f);
-          v[i] = (c < N) ? (v[i] + b) * kLog2e : -INFINITY;
-          mx = fmaxf(mx, v[i]);
+        for (int i = 0; i < CE_BN; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_cm[s][0][i]);
+          v[i] = fmaf(v[i], kLog2e, b4.x); v[i + 1] = fmaf(v[i + 1], kLog2e, b4.y);
+          v[i + 2] = fmaf(v[i + 2], kLog2e, b4.z); v[i + 3] = fmaf(v[i + 3], kLog2e, b4.w);
+          mx = fmaxf(fmaxf(mx, fmaxf(v[i], v[i + 1])), fmaxf(v[i + 2], v[i + 3]));
         }
         const float m_new = fmaxf(m_run, mx);
         float acc = 0.f;
@@ -209,23 +229,36 @@ ce_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUt
         for (int i = 0; i < CE_BN; ++i) acc += ex2(v[i] - m_new);
         l_run = l_run * ex2(m_run - m_new) + acc;
         m_run = m_new;
+      } else if (MODE == CE_BWD_U) {
+        const int rel = (row_tgt >= c0 && row_tgt < c0 + CE_BN) ? (int)(row_tgt - c0) : -1;
+#pragma unroll
+        for (int i = 0; i < CE_BN; i += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&s_cm[s][0][i]);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float e = ex2(fmaf(v[i + q], kLog2e, bb[q]) - row_lse2);       // 0 past the catalog (beta = -inf)
+            v[i + q] = tf32_rn(row_g * (e - ((i + q) == rel ? 1.f : 0.f)));
+          }
+        }
       } else {
 #pragma unroll
-        for (int i = 0; i < CE_BN; ++i) {
-          const long long c = c0 + i;
-          float x;
-          if (MODE == CE_BWD_U) {
-            const float b = guarded(p.beta, c, N, 0.f);
-            x = (c < N) ? row_g * (ex2((v[i] + b) * kLog2e - row_lse2) - ((int)c == row_tgt ? 1.f : 0.f)) : 0.f;
-          } else {
-            const float lse2 = guarded(p.lse, c, M, 0.f) * kLog2e;
-            const float gc = guarded(p.g, c, M, 0.f);
-            const int tc = guarded(p.tgt, c, M, -1);
-            x = (c < M && row < N) ? gc * (ex2((v[i] + row_beta) * kLog2e - lse2) - ((int)row == tc ? 1.f : 0.f)) : 0.f;
+        for (int i = 0; i < CE_BN; i += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(&s_cm[s][0][i]);
+          const float4 g4 = *reinterpret_cast<const float4*>(&s_cm[s][1][i]);
+          const int4 t4 = *reinterpret_cast<const int4*>(&s_ct[s][i]);
+          const float ll[4] = {l4.x, l4.y, l4.z, l4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+          const int tt[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float e = ex2(fmaf(v[i + q], kLog2e, row_beta2) - ll[q]);
+            const float x = gg[q] * (e - ((long long)tt[q] == row ? 1.f : 0.f));
             dbeta_acc += x;
+            v[i + q] = tf32_rn(x);
           }
-          v[i] = tf32_rn(x);
         }
+      }
+      if (MODE != CE_FWD) {
         // D tile as the K-major, 128-byte-swizzled A operand of the second MMA
         mbar_wait(smem_u32(&d_empty), ((uint32_t)j & 1u) ^ 1u);
 #pragma unroll

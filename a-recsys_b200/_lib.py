@@ -59,6 +59,10 @@ SIGNATURES = {
     'arx_ce_fwd': [vp, vp, vp, i64, i64, i64, vp, vp, vp],
     'arx_ce_bwd': [vp, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, vp, vp, vp, vp],
     'arx_ce_rowloss': [vp, vp, vp, vp, vp, i64, i64, i64, vp, vp],
+    'arx_mw_mask_words': [i64, vp],
+    'arx_mw_mask_build': [vp, vp, vp, i64, i64, vp, i64, vp],
+    'arx_mw_fwd': [vp, vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp],
+    'arx_mw_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp],
     'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
@@ -135,7 +139,7 @@ def call(name, *args):
     return rc
 
 
-_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd')
+_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd')
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 
@@ -221,3 +225,45 @@ def ce_bwd(U_r, P_r, beta, lse, g, target, M, N, d, dP=None):
             g.data_ptr(), target.data_ptr(), M, N, d, dU.data_ptr(), dP.data_ptr(), dbeta.data_ptr()) != 0:
         return None
     return dU, dP, dbeta
+
+
+def mw_mask_words(N):
+    n = ctypes.c_int64(0)
+    rc = load().arx_mw_mask_words(N, ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError('arx_mw_mask_words failed (%d)' % rc)
+    return n.value
+
+
+def mw_fwd(U_r, P_r, beta, tscore, mask, mask_ld, M, N, d):
+    """(hsum[M], loss[M]) of the sampled WMRB loss; scores never materialised.  None if unsupported."""
+    n = ctypes.c_int64(0)
+    rc = load().arx_ce_workspace_floats(M, N, ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError('arx_ce_workspace_floats failed (%d)' % rc)
+    ws = torch.empty(n.value, dtype=torch.float32, device=U_r.device)
+    hsum = torch.empty(M, dtype=torch.float32, device=U_r.device)
+    loss = torch.empty(M, dtype=torch.float32, device=U_r.device)
+    if call('arx_mw_fwd', U_r.data_ptr(), P_r.data_ptr(), ptr(beta), tscore.data_ptr(), ptr(mask), mask_ld, M, N, d,
+            ws.data_ptr(), hsum.data_ptr(), loss.data_ptr()) != 0:
+        return None
+    return hsum, loss
+
+
+def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None):
+    """(dU, dP, dbeta, dts) of sum_r g[r] * loss[r]."""
+    dev = U_r.device
+    UT = torch.empty((d, M), dtype=torch.float32, device=dev)
+    PT = torch.empty((d, N), dtype=torch.float32, device=dev)
+    call('arx_transpose', U_r.data_ptr(), M, d, UT.data_ptr(), 0)
+    call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
+    dU = torch.empty((M, d), dtype=torch.float32, device=dev)
+    if dP is None:
+        dP = torch.empty((N, d), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((N,), dtype=torch.float32, device=dev)
+    dts = torch.empty((M,), dtype=torch.float32, device=dev)
+    if call('arx_mw_bwd', U_r.data_ptr(), P_r.data_ptr(), UT.data_ptr(), PT.data_ptr(), ptr(beta), tscore.data_ptr(),
+            ptr(mask), mask_ld, hsum.data_ptr(), g.data_ptr(), M, N, d, dU.data_ptr(), dP.data_ptr(), dbeta.data_ptr(),
+            dts.data_ptr()) != 0:
+        return None
+    return dU, dP, dbeta, dts

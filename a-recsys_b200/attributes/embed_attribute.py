@@ -418,6 +418,33 @@ class EmbeddingAttribute(object):
             return None
         return loss, grads
 
+    def fused_mw(self, latent, Ps, bs, tscore, row_scale, want_grad, forward_only=False, pos_rows=None, dP=None):
+        """Sampled-pool scoring (:148-206, pool='sampled') + _compute_mw_loss (:641-649) + their gradients on the
+        tensor cores without writing the [rows, S] scores: arx_mw_mask_build / arx_mw_fwd / arx_mw_bwd.
+        Returns (loss_rows, (dU, dPs, dbs, dts) or None), or None when the shape is not supported."""
+        M, d, S = latent.shape[0], self.dim, Ps.shape[0]
+        if not _lib.ce_supported(M, S, d):
+            return None
+        key = 'mw' + ('_eval' if forward_only else '_train')
+        pos_ptr, pos_idx = self._positives(key)
+        pos_row = pos_rows if pos_rows is not None else self.u_indices['input']
+        ld = _lib.mw_mask_words(S)
+        mask = torch.empty((M, ld), dtype=torch.int32, device=self.device)
+        call('arx_mw_mask_build', pos_row.data_ptr(), pos_ptr.data_ptr(), pos_idx.data_ptr(), M, S, mask.data_ptr(), ld)
+        U_r = _lib.round_tf32(latent if latent.is_contiguous() else latent.contiguous())
+        P_r = _lib.round_tf32(Ps)
+        fw = _lib.mw_fwd(U_r, P_r, bs, tscore, mask, ld, M, S, d)
+        if fw is None:
+            return None
+        hsum, loss = fw
+        if not want_grad:
+            return loss, None
+        g = row_scale if row_scale is not None else torch.ones(M, dtype=torch.float32, device=self.device)
+        grads = _lib.mw_bwd(U_r, P_r, bs, tscore, mask, ld, hsum, g, M, S, d, dP=dP)
+        if grads is None:
+            return None
+        return loss, grads
+
     # -- embed_attribute.py:208-220 --------------------------------------------------------
     def get_target_score(self, latent, inds, device='/gpu:0'):
         ids = self._ids(inds)

@@ -257,16 +257,26 @@ class LatentProductModel(object):
             u = m.dropout(u0, keep_prob, masks[0] if masks else None)          # :78 / embed :236
             ctx = ('linear', m._last_user, keep_prob, getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None)
             S = Ps.shape[0]
-            logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
-            _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)               # :112
             tscore = torch.empty((mb,), dtype=torch.float32, device=self.device)
             call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), bt.data_ptr(), mb, self.size, tscore.data_ptr())   # :115
-            batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+            arena = dPt = None
             if train:
-                D, dts = logits, m._last_dtarget
                 arena = torch.empty((S + mb, self.size), dtype=torch.float32, device=self.device)
                 dPt = arena[S:]                   # both item-side gradients land in one arena: no concat
-                dU, dPs, dbs = self._scores_backward(D, u, Ps, dP=arena[:S])
+            # pool scoring + WMRB + adjoints fused on the tensor cores (:112, embed_attribute.py:641-649)
+            fused = m.fused_mw(u, Ps, bs, tscore, scale, train, dP=arena[:S] if train else None)
+            if fused is not None:
+                batch_loss, fg = fused
+                if train:
+                    dU, dPs, dbs, dts = fg
+            else:
+                logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
+                _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)           # :112
+                batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+                if train:
+                    D, dts = logits, m._last_dtarget
+                    dU, dPs, dbs = self._scores_backward(D, u, Ps, dP=arena[:S])
+            if train:
                 call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
                      dU.data_ptr(), dPt.data_ptr())
                 rng = m.sets[pre].attr_range()

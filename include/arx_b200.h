@@ -231,6 +231,25 @@ int arx_loss_rows(const float* scores, int64_t mb, int64_t V, int64_t ld,
                   float* loss, float* dscores, float* dtarget, int64_t* rank_out,
                   void* stream);
 
+/* K3 + K6 fused — sampled WMRB loss 'mw' over a pool of N items (embed_attribute.py:641-649 on the scores of
+ * :148-206, hmf_model.py:112-130) and its gradients, logits never materialised; same tcgen05 pipeline as arx_ce_*.
+ *   hinge[r, c] = max(0, 1 + U[r] . P[c] + beta[c] - tscore[r]) over the columns not excluded for row r
+ *   loss[r] = log(1 + hsum[r]),  hsum[r] = sum_c hinge[r, c]
+ *   D[r, c] = g[r] / (1 + hsum[r]) * [hinge[r, c] > 0];  dU = D P, dP = D^T U, dbeta = column sums, dts = -row sums
+ * mask: dense bit matrix [M, mask_ld] uint32, bit (r, c) = 1 excludes column c for row r (the user's other positives,
+ * the reference's tf.where(mask, ...) :646-647); arx_mw_mask_words gives mask_ld for N; arx_mw_mask_build zeroes it
+ * and sets the bits from the per-user CSR (pos_row[b] = user of batch row b or NULL, pos_idx = pool position or -1).
+ * workspace: arx_ce_workspace_floats(M, N) floats.  Shape limits as arx_ce_*. */
+int arx_mw_mask_words(int64_t N, int64_t* words_per_row);
+int arx_mw_mask_build(const int32_t* pos_row, const int32_t* pos_ptr, const int32_t* pos_idx, int64_t mb, int64_t N,
+                      uint32_t* mask, int64_t mask_ld, void* stream);
+int arx_mw_fwd(const float* U, const float* P, const float* beta, const float* tscore, const uint32_t* mask,
+               int64_t mask_ld, int64_t M, int64_t N, int64_t d, float* workspace, float* hsum, float* loss,
+               void* stream);
+int arx_mw_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
+               const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
+               int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, void* stream);
+
 /* K4 — target_score[b] = U[b].P[b] + beta[b] (embed_attribute.py:219-220) and its adjoint
  * dU[b] += dts[b] P[b]; dP[b] = dts[b] U[b]. */
 int arx_rowdot_fwd(const float* U, const float* P, const float* beta, int64_t mb, int dim,

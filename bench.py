@@ -356,13 +356,17 @@ def main():
                       'achieved_nominal': nbytes_nominal / us / 1e3, 'algorithmic_bytes': nbytes_unique,
                       'algorithmic_bytes_nominal': nbytes_nominal, 'avg_us': us, 'kernel': what, 'peak_source': peak_src}
     if world == 1:       # per-rank byte counts under sharding are 1/N of these: roofline only at N=1
-        roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_kernel<32,4> user side, 4096 bags')
+        roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_flat_kernel<1> user side, %d bags' % (a.mb * (a.n_mulhot + 1)))
         roof('arx_pool_bwd_apply:user', ub['bwd_unique'], ub['bwd_nominal'], 'pool_bwd_apply_kernel<4> user side')
     dom = max(roofs, key=lambda k: per_kernel[k]['ms_per_step']) if roofs else None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
-    if os.path.exists(tpath):    # dram bytes per launch from the committed ncu --set full capture
+    # dram bytes per launch from the committed ncu --set full capture (profiles/r1_ncu_summary.md; the first
+    # launch of each kernel in the eager step is the user side)
+    tkeys = {'arx_pool_fwd:user': 'void pool_fwd_flat_kernel<1> grid %d #1' % ((a.mb + 6) // 7),
+             'arx_pool_bwd_apply:user': 'void pool_bwd_apply_kernel<4> grid 592 #1'}
+    if os.path.exists(tpath):
         for k, r in roofs.items():
-            t = json.load(open(tpath)).get(r['kernel'])
+            t = json.load(open(tpath)).get(tkeys.get(k, ''))
             if t:
                 r['traffic'] = t['dram_bytes_read'] + t['dram_bytes_write']
                 r['traffic_source'] = t['source']

@@ -1,14 +1,22 @@
 """NumPy oracle for the A-RecSys training hot path.  TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: the reference (skywaLKer518/A-Recsys) ships no tests, no golden
-vectors and cannot run here (Python 2 + TensorFlow 1.0, neither installed).  This
-file is a CPU restatement of the reference's *op sequence* (cited file:line below,
-paths relative to the reference root), anchored on (a) the hand-checked known-answer
-vectors of SURVEY.md section 8(c) (tests/test_oracle_kat.py), (b) dataset-derived
-facts of the bundled MovieLens-1m files (tests/golden/ml1m_facts.json) and (c) a
-second, independent derivation of every gradient through torch-CPU float64 autograd
-(oracle/torch_cpu_ref.py).  The TensorFlow-1.0 op semantics used
-are restated from the public TF docs and are not verifiable offline.
+HOW THIS ORACLE IS PINNED: the reference (skywaLKer518/A-Recsys) ships no tests and no
+golden vectors and cannot run as published (Python 2 + TensorFlow 1.0, neither
+installable offline).  Its model code parses under Python 3, so
+tests/golden/make_ref_golden.py runs the UNMODIFIED reference sources
+(hmf/hmf_model.py, lstm/seqModel.py, word2vec/cbow_model.py, attributes/
+embed_attribute.py, mulhot_index.py, attribute.py) on oracle/tf1_shim (a lazy-graph
+restatement of the TF-1.0 ops they call) and commits what the reference's own graphs
+compute as tests/golden/ref_*.npz; tests/test_ref_golden.py holds this oracle (and
+the CUDA path) to those vectors.  Scope of the pin: op ORDER and model wiring are the
+reference's own code; the per-op TensorFlow-1.0 semantics are
+restated in the shim from the public TF docs and are not verifiable offline.
+This file is a CPU restatement of the reference's *op sequence* (cited file:line below,
+paths relative to the reference root), additionally anchored on (a) the hand-checked
+known-answer vectors of SURVEY.md section 8(c) (tests/test_oracle_kat.py), (b)
+dataset-derived facts of the bundled MovieLens-1m files (tests/golden/ml1m_facts.json)
+and (c) a second, independent derivation of every gradient through torch-CPU float64
+autograd (oracle/torch_cpu_ref.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
 legs may import this package.  The product (a-recsys_b200/) never does.

@@ -1,5 +1,6 @@
 """PyTorch-CPU restatement of the reference HMF training step.  TEST / BASELINE INFRASTRUCTURE
-ONLY (see oracle/np_oracle.py header; PARITY UNPINNED for the same reasons).
+ONLY (see oracle/np_oracle.py header for how the oracle is pinned: golden vectors produced by the
+reference's own model code on oracle/tf1_shim, tests/test_ref_golden.py).
 
 Executes the reference's op sequence *literally* (index_select -> segment-sum (index_add_) ->
 div -> mean over attributes -> dropout -> token-score matmul -> index_select -> segment-sum ->

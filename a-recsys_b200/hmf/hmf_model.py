@@ -287,14 +287,21 @@ class LatentProductModel(object):
             pre = m._out_prefix()
             Ps, bs, sids = m.pool_catalog('sampled')                           # :112
             S = Ps.shape[0]
-            logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
-            _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)
             tscore = m.get_target_score(u, item_ids)                           # :115
             _, Pt, _ = m._last_target
-            batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+            fused = m.fused_mw(u, Ps, bs, tscore, scale, train)
+            if fused is not None:
+                batch_loss, fg = fused
+                if train:
+                    dU, dPs, dbs, dts = fg
+            else:
+                logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
+                _lib.gemm(u, Ps, logits, mb, S, self.size, 0, 1, bs)
+                batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+                if train:
+                    D, dts = logits, m._last_dtarget
+                    dU, dPs, dbs = self._scores_backward(D, u, Ps)
             if train:
-                D, dts = logits, m._last_dtarget
-                dU, dPs, dbs = self._scores_backward(D, u, Ps)
                 dPt = torch.empty_like(Pt)
                 call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size,
                      dU.data_ptr(), dPt.data_ptr())

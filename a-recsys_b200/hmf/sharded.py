@@ -66,16 +66,20 @@ class ShardedLatentProductModel(LatentProductModel):
         keep = self.dropout
         u = m.dropout(U0, keep, masks[0] if masks else None)
         dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
-        logits = torch.empty((mb, S), dtype=torch.float32, device=dev)
-        _lib.gemm(u, Ps, logits, mb, S, d, 0, 1, bsl)
         tscore = torch.empty((mb,), dtype=torch.float32, device=dev)
         call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), btl.data_ptr(), mb, d, tscore.data_ptr())
         scale = self._scale(n_g)[:mb]                                   # 1 / (G*mb): global batch mean
-        bl = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=True, pos_rows=users_l)
+        fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l)
+        if fused is not None:                                           # scoring + WMRB + adjoints on the tensor cores
+            bl, (dU, dPs, dbs, dts) = fused
+        else:
+            logits = torch.empty((mb, S), dtype=torch.float32, device=dev)
+            _lib.gemm(u, Ps, logits, mb, S, d, 0, 1, bsl)
+            bl = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=True, pos_rows=users_l)
+            # ---- backward: one AR + one AG, then local sparse Adagrad ----------------------------
+            D, dts = logits, m._last_dtarget
+            dU, dPs, dbs = self._scores_backward(D, u, Ps)
         loss_sum = (bl.sum() / n_g).reshape(1)
-        # ---- backward: one AR + one AG, then local sparse Adagrad --------------------------------
-        D, dts = logits, m._last_dtarget
-        dU, dPs, dbs = self._scores_backward(D, u, Ps)
         dPt = torch.empty_like(Pt)
         call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, d, dU.data_ptr(), dPt.data_ptr())
         if keep != 1.0:

@@ -106,11 +106,15 @@ class Model(object):
         if eff == 'mw':
             Ps, bs, sids = m.pool_catalog('sampled', self.output_feat)
             S = Ps.shape[0]
-            logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
-            _lib.gemm(h, Ps, logits, mb, S, self.size, 0, 1, bs)
             tscore = m.get_target_score(h, out_ids)
             Pt = m._last_target[1]
-            batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
+            fused = m.fused_mw(h, Ps, bs, tscore, scale, train)     # scoring + WMRB + adjoints on the tensor cores
+            if fused is not None:
+                batch_loss, fgrads = fused
+            else:
+                logits = torch.empty((mb, S), dtype=torch.float32, device=self.device)
+                _lib.gemm(h, Ps, logits, mb, S, self.size, 0, 1, bs)
+                batch_loss = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=train)
             P = Ps
         else:
             fused = m.fused_ce(h, targets, scale, train, 'full', self.output_feat) if eff == 'ce' else None
@@ -124,7 +128,7 @@ class Model(object):
         loss_val = batch_loss.mean()
         if train:
             if fused is not None:
-                dH, dP, db = fgrads
+                dH, dP, db = fgrads[:3]
             else:
                 D = logits
                 N = D.shape[1]
@@ -137,7 +141,7 @@ class Model(object):
             rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
             m.push_grad(pre, rng_out, sids, POOL_MEAN, dP, db, plan_key='catalog' if eff != 'mw' else None)
             if eff == 'mw':
-                dts = m._last_dtarget
+                dts = fgrads[3] if fused is not None else m._last_dtarget
                 dPt = torch.empty_like(Pt)
                 call('arx_rowdot_bwd', h.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, self.size, dH.data_ptr(),
                      dPt.data_ptr())

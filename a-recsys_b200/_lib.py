@@ -65,6 +65,8 @@ SIGNATURES = {
     'arx_mw_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp],
     'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    'arx_lstm_gates_fwd2': [vp, vp, vp, vp, vp, i64, i32, f32, vp],
+    'arx_lstm_gates_bwd2': [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
     'arx_sum_over_steps': [vp, i64, i64, i32, f32, vp, vp],
     'arx_transpose': [vp, i64, i64, vp, i32, vp],

@@ -12,9 +12,15 @@ namespace {
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // Z [mb, 4H]: pre-activations in, activated gates (i, j, f, o) out (kept for the backward pass)
+__device__ __forceinline__ float round_tf32(float x) {      // nearest tf32 (10-bit mantissa), ties away
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
 __global__ void lstm_gates_fwd_kernel(float* __restrict__ Z, const float* __restrict__ c_prev,
                                       float* __restrict__ c, float* __restrict__ h, long long mb, int H,
-                                      float forget_bias) {
+                                      float forget_bias, float* __restrict__ h_tf32) {
   const long long n = mb * H;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
@@ -29,7 +35,9 @@ __global__ void lstm_gates_fwd_kernel(float* __restrict__ Z, const float* __rest
     const float cn = f * cp + i * j;
     z[k] = i; z[H + k] = j; z[2 * H + k] = f; z[3 * H + k] = o;
     c[idx] = cn;
-    h[idx] = o * tanhf(cn);
+    const float hn = o * tanhf(cn);
+    h[idx] = hn;
+    if (h_tf32) h_tf32[idx] = round_tf32(hn);       // the A operand of the next step's h W_h contraction
   }
 }
 
@@ -38,7 +46,7 @@ __global__ void lstm_gates_fwd_kernel(float* __restrict__ Z, const float* __rest
 __global__ void lstm_gates_bwd_kernel(float* __restrict__ G, const float* __restrict__ c_prev,
                                       const float* __restrict__ c, const float* __restrict__ dh_out,
                                       const float* __restrict__ dh_rec, const float* __restrict__ dc_next,
-                                      float* __restrict__ dc_prev, long long mb, int H) {
+                                      float* __restrict__ dc_prev, long long mb, int H, int round_out) {
   const long long n = mb * H;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
@@ -50,10 +58,10 @@ __global__ void lstm_gates_bwd_kernel(float* __restrict__ G, const float* __rest
     const float tc = tanhf(c[idx]);
     const float dc = dh * o * (1.0f - tc * tc) + (dc_next ? dc_next[idx] : 0.f);
     const float cp = c_prev ? c_prev[idx] : 0.f;
-    g[k] = dc * j * i * (1.0f - i);
-    g[H + k] = dc * i * (1.0f - j * j);
-    g[2 * H + k] = dc * cp * f * (1.0f - f);
-    g[3 * H + k] = dh * tc * o * (1.0f - o);
+    float g0 = dc * j * i * (1.0f - i), g1 = dc * i * (1.0f - j * j), g2 = dc * cp * f * (1.0f - f),
+          g3 = dh * tc * o * (1.0f - o);
+    if (round_out) { g0 = round_tf32(g0); g1 = round_tf32(g1); g2 = round_tf32(g2); g3 = round_tf32(g3); }
+    g[k] = g0; g[H + k] = g1; g[2 * H + k] = g2; g[3 * H + k] = g3;   // dZ only feeds tensor-core contractions
     dc_prev[idx] = dc * f;
   }
 }
@@ -94,11 +102,28 @@ inline int ew_grid(long long n) {
 
 }  // namespace
 
-extern "C" int arx_lstm_gates_fwd(float* Z, const float* c_prev, float* c, float* h, int64_t mb, int H,
-                                  float forget_bias, void* stream) {
+extern "C" int arx_lstm_gates_fwd2(float* Z, const float* c_prev, float* c, float* h, float* h_tf32, int64_t mb,
+                                   int H, float forget_bias, void* stream) {
   if (!Z || !c || !h || mb < 0 || H < 1) return ARX_E_BADARG;
   if (mb == 0) return ARX_OK;
-  lstm_gates_fwd_kernel<<<ew_grid(mb * H), 256, 0, (cudaStream_t)stream>>>(Z, c_prev, c, h, mb, H, forget_bias);
+  lstm_gates_fwd_kernel<<<ew_grid(mb * H), 256, 0, (cudaStream_t)stream>>>(Z, c_prev, c, h, mb, H, forget_bias,
+                                                                           h_tf32);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+extern "C" int arx_lstm_gates_fwd(float* Z, const float* c_prev, float* c, float* h, int64_t mb, int H,
+                                  float forget_bias, void* stream) {
+  return arx_lstm_gates_fwd2(Z, c_prev, c, h, nullptr, mb, H, forget_bias, stream);
+}
+
+extern "C" int arx_lstm_gates_bwd2(float* G, const float* c_prev, const float* c, const float* dh_out,
+                                   const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
+                                   int round_tf32_out, void* stream) {
+  if (!G || !c || !dc_prev || mb < 0 || H < 1) return ARX_E_BADARG;
+  if (mb == 0) return ARX_OK;
+  lstm_gates_bwd_kernel<<<ew_grid(mb * H), 256, 0, (cudaStream_t)stream>>>(G, c_prev, c, dh_out, dh_rec, dc_next,
+                                                                           dc_prev, mb, H, round_tf32_out);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }
@@ -106,12 +131,7 @@ extern "C" int arx_lstm_gates_fwd(float* Z, const float* c_prev, float* c, float
 extern "C" int arx_lstm_gates_bwd(float* G, const float* c_prev, const float* c, const float* dh_out,
                                   const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
                                   void* stream) {
-  if (!G || !c || !dc_prev || mb < 0 || H < 1) return ARX_E_BADARG;
-  if (mb == 0) return ARX_OK;
-  lstm_gates_bwd_kernel<<<ew_grid(mb * H), 256, 0, (cudaStream_t)stream>>>(G, c_prev, c, dh_out, dh_rec, dc_next,
-                                                                           dc_prev, mb, H);
-  ARX_CHECK_LAUNCH();
-  return ARX_OK;
+  return arx_lstm_gates_bwd2(G, c_prev, c, dh_out, dh_rec, dc_next, dc_prev, mb, H, 0, stream);
 }
 
 extern "C" int arx_axpby_rows(const float* x1, const float* x2_rows, float a, float b, int64_t rows,

@@ -58,11 +58,17 @@ class LSTMLayer(object):
         _lib.gemm(Xd.view(T * mb, d_in), WxT, G.view(T * mb, 4 * H), T * mb, 4 * H, d_in, 0, 1, self.b, b_ready=True)
         Hs = torch.zeros((T + 1, mb, H), dtype=torch.float32, device=dev)      # Hs[t] = h_{t-1}
         Cs = torch.zeros((T + 1, mb, H), dtype=torch.float32, device=dev)
+        tc = not _lib.exact_fp32
+        # tensor-core path: the gate kernel also emits the tf32-rounded h (the next step's A operand),
+        # instead of one arx_round_tf32 launch per step
+        Hr = torch.empty((2, mb, H), dtype=torch.float32, device=dev) if tc else None
         for t in range(T):
             if t > 0:
-                _lib.gemm(Hs[t], WhT, G[t], mb, 4 * H, H, 0, 1, None, 1.0, 1.0, b_ready=True)
-            call('arx_lstm_gates_fwd', G[t].data_ptr(), Cs[t].data_ptr() if t > 0 else None,
-                 Cs[t + 1].data_ptr(), Hs[t + 1].data_ptr(), mb, H, self.forget_bias)
+                _lib.gemm(Hr[t & 1] if tc else Hs[t], WhT, G[t], mb, 4 * H, H, 0, 1, None, 1.0, 1.0,
+                          a_ready=tc, b_ready=True)
+            call('arx_lstm_gates_fwd2', G[t].data_ptr(), Cs[t].data_ptr() if t > 0 else None,
+                 Cs[t + 1].data_ptr(), Hs[t + 1].data_ptr(), Hr[(t + 1) & 1].data_ptr() if tc else None,
+                 mb, H, self.forget_bias)
         out = Hs[1:]
         if keep != 1.0:
             if out_mask is None:
@@ -84,19 +90,23 @@ class LSTMLayer(object):
             call('arx_scale_mask', dOut.data_ptr(), out_mask.data_ptr(), 1.0 / keep, dOut.numel(), dH.data_ptr())
         else:
             dH = dOut.contiguous()
+        tc = not _lib.exact_fp32
         Wh = self.W[d_in:]                                   # [H, 4H] = the K-major B of dZ W_h^T
+        if tc:                                               # rounded once, not once per step
+            Wh = _lib.round_tf32(Wh.contiguous())
         dh_rec = torch.empty((mb, H), dtype=torch.float32, device=dev)
         dc = [torch.empty((mb, H), dtype=torch.float32, device=dev) for _ in range(2)]
         for t in range(T - 1, -1, -1):
             last = (t == T - 1)
-            call('arx_lstm_gates_bwd', G[t].data_ptr(), Cs[t].data_ptr() if t > 0 else None, Cs[t + 1].data_ptr(),
+            # dZ is written tf32-rounded on the tensor-core path: it only feeds contractions
+            call('arx_lstm_gates_bwd2', G[t].data_ptr(), Cs[t].data_ptr() if t > 0 else None, Cs[t + 1].data_ptr(),
                  dH[t].data_ptr(), None if last else dh_rec.data_ptr(), None if last else dc[(t + 1) & 1].data_ptr(),
-                 dc[t & 1].data_ptr(), mb, H)
+                 dc[t & 1].data_ptr(), mb, H, 1 if tc else 0)
             if t > 0:
-                _lib.gemm(G[t], Wh, dh_rec, mb, H, 4 * H, 0, 1)
+                _lib.gemm(G[t], Wh, dh_rec, mb, H, 4 * H, 0, 1, a_ready=tc, b_ready=tc)
         dZ = G.view(T * mb, 4 * H)
         dX = torch.empty((T * mb, d_in), dtype=torch.float32, device=dev)
-        _lib.gemm(dZ, self.W[:d_in], dX, T * mb, d_in, 4 * H, 0, 1)
+        _lib.gemm(dZ, self.W[:d_in], dX, T * mb, d_in, 4 * H, 0, 1, a_ready=tc)
         _lib.gemm(Xd.view(T * mb, d_in), dZ, self.dW[:d_in], d_in, 4 * H, T * mb, 1, 0)
         _lib.gemm(Hs[:T].view(T * mb, H), dZ, self.dW[d_in:], H, 4 * H, T * mb, 1, 0)
         call('arx_colsum', dZ.data_ptr(), T * mb, 4 * H, 4 * H, self.db.data_ptr())

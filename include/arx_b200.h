@@ -270,6 +270,14 @@ int arx_lstm_gates_fwd(float* Z, const float* c_prev, float* c, float* h, int64_
 int arx_lstm_gates_bwd(float* G, const float* c_prev, const float* c, const float* dh_out,
                        const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
                        void* stream);
+/* Same, with the tf32 rounding of the tensor-core operands fused in: fwd2 also writes h_tf32 (the A operand of
+ * the next step's h W_h contraction; NULL = skip), bwd2 rounds dZ in place when round_tf32_out != 0 (dZ only
+ * feeds contractions).  Saves one arx_round_tf32 launch per time step and direction. */
+int arx_lstm_gates_fwd2(float* Z, const float* c_prev, float* c, float* h, float* h_tf32, int64_t mb, int H,
+                        float forget_bias, void* stream);
+int arx_lstm_gates_bwd2(float* G, const float* c_prev, const float* c, const float* dh_out,
+                        const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
+                        int round_tf32_out, void* stream);
 /* K9 — LSTM / CBOW input mixing: y[r,:] = a*x1[r,:] + b*x2[r % rep,:] (reduce_mean([user_embed,
  * item_embed], 0), lstm/seqModel.py:155; x2 broadcast over the T steps) and the adjoint of the
  * broadcast: out[r,:] = scale * sum_t x[t*rep + r,:]. */

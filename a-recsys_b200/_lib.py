@@ -104,6 +104,10 @@ def load():
     lib.arx_build_info.argtypes = []
     lib.arx_build_info.restype = ctypes.c_char_p
     _lib = lib
+    for kv in filter(None, os.environ.get('ARX_TUNE', '').split(',')):     # e.g. ARX_TUNE=plan_agg=1,flat_epb=5
+        k, v = kv.split('=')
+        if lib.arx_set_tuning(k.encode(), int(v)) != 0:
+            raise RuntimeError('ARX_TUNE: bad setting %r' % kv)
     return lib
 
 

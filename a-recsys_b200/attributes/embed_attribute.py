@@ -312,11 +312,21 @@ class EmbeddingAttribute(object):
         if keep_prob == 1.0:
             return x
         if mask is None:
-            mask = torch.floor(torch.rand_like(x) + keep_prob)
+            mask = getattr(self, '_premade_mask', None)
+            self._premade_mask = None
+            if mask is None or mask.shape != x.shape:
+                mask = torch.floor(torch.rand_like(x) + keep_prob)
         y = torch.empty_like(x)
         call('arx_scale_mask', x.data_ptr(), mask.data_ptr(), 1.0 / keep_prob, x.numel(), y.data_ptr())
         self._last_dropout_mask = mask
         return y
+
+    def premake_dropout_mask(self, shape, keep_prob):
+        """Draw the next dropout mask now (it depends on nothing): the three tiny generator kernels then sit
+        in front of the lookups instead of on the dependent chain behind them."""
+        self._premade_mask = None
+        if keep_prob != 1.0:
+            self._premade_mask = torch.floor(torch.rand(shape, dtype=torch.float32, device=self.device) + keep_prob)
 
     # -- embed_attribute.py:239-254 --------------------------------------------------------
     def get_batch_item(self, name, batch_size, concat=False, keep_prob=1.0, no_attribute=False,
@@ -774,10 +784,13 @@ class EmbeddingAttribute(object):
             main.wait_stream(side)
 
     def side_stream(self, k):
+        """Streams 8.. carry the backward-plan builds: thousands of small latency-bound CTAs that would
+        otherwise take the SM slots the dependent chain of the step is waiting for (torch.profiler timeline,
+        tools/trace_step.py) — they get the LOW priority, every other stream of the step the high one."""
         if not hasattr(self, '_side_streams'):
             self._side_streams = {}
         if k not in self._side_streams:
-            self._side_streams[k] = torch.cuda.Stream(device=self.device)
+            self._side_streams[k] = torch.cuda.Stream(device=self.device, priority=0 if k >= 8 else -1)
         return self._side_streams[k]
 
     def pool_many(self, requests):

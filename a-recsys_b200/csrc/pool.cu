@@ -514,6 +514,189 @@ plan_fill_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int 
   }
 }
 
+// ---- block-aggregated plan kernels --------------------------------------------------------------
+// The warp-per-bag kernels above issue one global atomic per OCCURRENCE on touch[token]; with Zipf tokens the
+// head token of every multi-hot table takes ~8 % of them (32 k same-address atomics per launch at C2), which
+// serialise in L2 and stretch these kernels to 35-55 us right where the step's dependent chain needs the SMs
+// (tools/trace_step.py).  Here a CTA resolves a group of <= 64 bags block-wide (as pool_fwd_flat_kernel does),
+// aggregates its occurrences per (table, token) in a shared-memory hash table and issues ONE global atomic per
+// distinct token of the group: the head tokens drop from one atomic per occurrence to one per CTA.
+constexpr int kAggBags = 64;
+constexpr int kAggRows = 1024;                 // occurrences per hash round
+constexpr int kAggSlots = 2048;                // hash slots (load factor <= 0.5)
+constexpr unsigned kAggEmpty = 0xffffffffu;
+
+__device__ __forceinline__ int agg_insert(unsigned* keys, unsigned key) {
+  unsigned slot = (key * 2654435761u) >> 21;   // 11 bits
+  while (true) {
+    const unsigned prev = atomicCAS(&keys[slot], kAggEmpty, key);
+    if (prev == kAggEmpty || prev == key) return (int)slot;
+    slot = (slot + 1) & (kAggSlots - 1);
+  }
+}
+
+struct AggShared {
+  arx_attr_desc attrs[kMaxAttr];
+  int start[kAggBags], len[kAggBags], lenf[kAggBags], off[kAggBags + 1];
+  unsigned keys[kAggSlots];
+  int cnt[kAggSlots];
+  int base[kAggSlots];
+  int n_first, first_base;
+};
+
+// bag extents of entities [e0, e0 + ne) x n_attr attributes -> sh.start/len/lenf/off; returns the row count
+__device__ __forceinline__ int agg_resolve(AggShared& sh, int n_attr, const int* __restrict__ ids, long long e0, int ne) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = ne * n_attr;
+  if (tid < nb) {
+    const int el = tid / n_attr, f = tid - el * n_attr;
+    const int e = __ldg(ids + e0 + el);
+    int s = e, L = 1, Lf = 1;
+    if (sh.attrs[f].kind == 1) {
+      s = __ldg(sh.attrs[f].starts + e); L = __ldg(sh.attrs[f].lengths + e); Lf = full_len(sh.attrs[f], e, L);
+    }
+    sh.start[tid] = s; sh.len[tid] = L; sh.lenf[tid] = Lf;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int a = (lane < nb) ? sh.len[lane] : 0, b = (lane + 32 < nb) ? sh.len[lane + 32] : 0;
+    int ia = a, ib = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int ta = __shfl_up_sync(ARX_FULL_MASK, ia, o), tb = __shfl_up_sync(ARX_FULL_MASK, ib, o);
+      if (lane >= o) { ia += ta; ib += tb; }
+    }
+    const int tot_a = __shfl_sync(ARX_FULL_MASK, ia, 31);
+    if (lane < nb) sh.off[lane] = ia - a;
+    if (lane + 32 < nb) sh.off[lane + 32] = tot_a + ib - b;
+    if (lane == 31) sh.off[nb] = tot_a + ib;
+  }
+  __syncthreads();
+  return sh.off[nb];
+}
+
+// row r of the group -> (bag, token); returns false when the row is not owned by this GPU
+__device__ __forceinline__ bool agg_row(const AggShared& sh, int n_attr, int nb, int r, int& bag, int& f, int& tok) {
+  int lo = 0, hi = nb;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh.off[mid] <= r) lo = mid; else hi = mid; }
+  bag = lo; f = lo % n_attr;
+  tok = __ldg(sh.attrs[f].values + sh.start[lo] + (r - sh.off[lo]));
+  return owns(shard_of(sh.attrs[f]), tok);
+}
+
+__global__ void __launch_bounds__(256)
+plan_count_agg_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int n_attr,
+                      const int* __restrict__ ids, long long n, arx_bwd_plan plan, int epb) {
+  __shared__ AggShared sh;
+  stage_descs(sh.attrs, g_attrs + attr_begin, n_attr);
+  const int tid = threadIdx.x;
+  for (long long e0 = (long long)blockIdx.x * epb; e0 < n; e0 += (long long)gridDim.x * epb) {
+    const int ne = (int)min((long long)epb, n - e0);
+    const int nb = ne * n_attr;
+    const int R = agg_resolve(sh, n_attr, ids, e0, ne);
+    for (int rb = 0; rb < R; rb += kAggRows) {
+      for (int i = tid; i < kAggSlots; i += blockDim.x) { sh.keys[i] = kAggEmpty; sh.cnt[i] = 0; }
+      if (tid == 0) sh.n_first = 0;
+      __syncthreads();
+      const int re = min(R, rb + kAggRows);
+      for (int r = rb + tid; r < re; r += blockDim.x) {
+        int bag, f, tok;
+        if (agg_row(sh, n_attr, nb, r, bag, f, tok)) atomicAdd(&sh.cnt[agg_insert(sh.keys, ((unsigned)f << 27) | (unsigned)tok)], 1);
+      }
+      __syncthreads();
+      // one global atomic per distinct (table, token) of the group; first-touch rows join the unique list
+      int myfirst[kAggSlots / 256];
+      int nf = 0;
+#pragma unroll
+      for (int q = 0; q < kAggSlots / 256; ++q) {          // all global atomics in flight before any result is used
+        const int i = q * 256 + tid;
+        const unsigned key = sh.keys[i];
+        myfirst[q] = 1;
+        if (key != kAggEmpty) myfirst[q] = atomicAdd(&sh.attrs[key >> 27].touch[key & 0x7ffffffu], sh.cnt[i]);
+      }
+#pragma unroll
+      for (int q = 0; q < kAggSlots / 256; ++q) {
+        if (myfirst[q] == 0) { myfirst[q] = atomicAdd(&sh.n_first, 1); ++nf; }
+        else myfirst[q] = -1;
+      }
+      __syncthreads();
+      if (tid == 0 && sh.n_first > 0) sh.first_base = atomicAdd(&plan.counters[0], sh.n_first);
+      __syncthreads();
+      if (nf > 0) {
+#pragma unroll
+        for (int q = 0; q < kAggSlots / 256; ++q) {
+          if (myfirst[q] < 0) continue;
+          const unsigned key = sh.keys[q * 256 + tid];
+          const int u = sh.first_base + myfirst[q];
+          if (u < plan.cap_rows) { plan.uniq_tok[u] = (int)(key & 0x7ffffffu); plan.uniq_attr[u] = attr_begin + (int)(key >> 27); }
+          else plan.counters[2] = 1;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+plan_fill_agg_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int n_attr,
+                     const int* __restrict__ ids, long long n, int mode, long long row_base,
+                     arx_bwd_plan plan, int epb) {
+  __shared__ AggShared sh;
+  stage_descs(sh.attrs, g_attrs + attr_begin, n_attr);
+  if (plan.counters[2] != 0) return;        // capacity exceeded: leave buckets untouched
+  const int tid = threadIdx.x;
+  const float invF = (mode == ARX_POOL_MEAN) ? 1.0f / (float)n_attr : 1.0f;
+  for (long long e0 = (long long)blockIdx.x * epb; e0 < n; e0 += (long long)gridDim.x * epb) {
+    const int ne = (int)min((long long)epb, n - e0);
+    const int nb = ne * n_attr;
+    const int R = agg_resolve(sh, n_attr, ids, e0, ne);
+    for (int rb = 0; rb < R; rb += kAggRows) {
+      for (int i = tid; i < kAggSlots; i += blockDim.x) { sh.keys[i] = kAggEmpty; sh.cnt[i] = 0; }
+      __syncthreads();
+      const int re = min(R, rb + kAggRows);
+      int slot_[kAggRows / 256], rank_[kAggRows / 256], row_[kAggRows / 256];
+      float w_[kAggRows / 256];
+#pragma unroll
+      for (int q = 0; q < kAggRows / 256; ++q) {
+        const int r = rb + q * 256 + tid;
+        slot_[q] = -1;
+        if (r < re) {
+          int bag, f, tok;
+          if (agg_row(sh, n_attr, nb, r, bag, f, tok)) {
+            slot_[q] = agg_insert(sh.keys, ((unsigned)f << 27) | (unsigned)tok);
+            rank_[q] = atomicAdd(&sh.cnt[slot_[q]], 1);
+            const long long ei = e0 + bag / n_attr;
+            row_[q] = (mode == ARX_POOL_MEAN) ? (int)(row_base + ei) : (int)(row_base + ei * n_attr + f);
+            w_[q] = invF / (float)sh.lenf[bag];
+          }
+        }
+      }
+      __syncthreads();
+      {                                                           // reserve cnt consecutive bucket slots per token
+        int b_[kAggSlots / 256];
+#pragma unroll
+        for (int q = 0; q < kAggSlots / 256; ++q) {               // independent atomics, all in flight together
+          const int i = q * 256 + tid;
+          const unsigned key = sh.keys[i];
+          b_[q] = 0;
+          if (key != kAggEmpty) b_[q] = atomicAdd(&sh.attrs[key >> 27].touch[key & 0x7ffffffu], sh.cnt[i]);
+        }
+#pragma unroll
+        for (int q = 0; q < kAggSlots / 256; ++q) sh.base[q * 256 + tid] = b_[q];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < kAggRows / 256; ++q) {
+        if (slot_[q] < 0) continue;
+        const int pos = sh.base[slot_[q]] + rank_[q];
+        plan.bucket_src[pos] = row_[q];
+        plan.bucket_w[pos] = w_[q];
+      }
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void plan_reset_kernel(const arx_attr_desc* __restrict__ g_attrs, arx_bwd_plan plan) {
   const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
   for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < nu; u += gridDim.x * blockDim.x)
@@ -806,6 +989,7 @@ rows_sumsq_kernel(const float* __restrict__ rows, const float* __restrict__ brow
 
 int g_tune_flat_epb = 0;         // arx_set_tuning("flat_epb", 0 = auto | 1..16): entities per CTA of the flat forward
 int g_tune_apply_cps = 4;        // arx_set_tuning("apply_ctas_per_sm", 1..4)
+int g_tune_plan_agg = 3;         // arx_set_tuning("plan_agg", 0 | 1): block-aggregated plan_count / plan_fill (tables < 2^27 rows)
 
 inline int pick_grid(long long warps_needed, int threads) {
   const int sms = arx_num_sms();
@@ -914,6 +1098,12 @@ extern "C" int arx_bwd_plan_count(const arx_attr_desc* attrs, int attr_begin, in
   if (!attrs || !ent_ids || attr_begin < 0 || n_attr < 1 || n_attr > kMaxAttr || n < 0 || !plan_args_ok(plan))
     return ARX_E_BADARG;
   if (n == 0) return ARX_OK;
+  if (g_tune_plan_agg & 1) {
+    const int epb = std::max(1, kAggBags / n_attr);
+    const long long blocks = (n + epb - 1) / epb;
+    const int grid = (int)std::min(blocks, (long long)arx_num_sms() * 16);
+    plan_count_agg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids, (long long)n, plan, epb);
+  } else
   plan_count_kernel<<<pick_grid(n * n_attr, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
                                                                         (long long)n, plan);
   ARX_CHECK_LAUNCH();
@@ -934,6 +1124,13 @@ extern "C" int arx_bwd_plan_fill(const arx_attr_desc* attrs, int attr_begin, int
     return ARX_E_BADARG;
   if (mode != ARX_POOL_MEAN && mode != ARX_POOL_CONCAT) return ARX_E_BADARG;
   if (n == 0) return ARX_OK;
+  if (g_tune_plan_agg & 2) {
+    const int epb = std::max(1, kAggBags / n_attr);
+    const long long blocks = (n + epb - 1) / epb;
+    const int grid = (int)std::min(blocks, (long long)arx_num_sms() * 16);
+    plan_fill_agg_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids, (long long)n, mode,
+                                                                (long long)row_base, plan, epb);
+  } else
   plan_fill_kernel<<<pick_grid(n * n_attr, 256), 256, 0, (cudaStream_t)stream>>>(attrs, attr_begin, n_attr, ent_ids,
                                                                        (long long)n, mode, (long long)row_base, plan);
   ARX_CHECK_LAUNCH();
@@ -984,6 +1181,10 @@ extern "C" int arx_set_tuning(const char* key, int value) {
   if (eq("flat_epb")) {
     if (value < 0 || value > kFlatEnt) return ARX_E_BADARG;
     g_tune_flat_epb = value;
+    return ARX_OK;
+  }
+  if (eq("plan_agg")) {
+    g_tune_plan_agg = value & 3;          // bit 0: count, bit 1: fill
     return ARX_OK;
   }
   if (eq("apply_ctas_per_sm")) {

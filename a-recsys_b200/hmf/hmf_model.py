@@ -229,9 +229,10 @@ class LatentProductModel(object):
             return idx.cpu().numpy()                                           # :154,:200
 
         item_ids = m._ids(item_input)
-        targets = m.item2logit_dev[item_ids.long()].contiguous()               # target_mapping :173
         train = not forward_only
         eff = loss if loss is not None else self.loss_function
+        # target_mapping :173 (the sampled loss scores the target items directly and never reads it)
+        targets = m.item2logit_dev[item_ids.long()].contiguous() if (eff != 'mw' or forward_only) else None
         unmasked = False
         if eff == 'mw' and forward_only:
             eff = 'warp'                                                       # loss_eval :130,:144
@@ -245,14 +246,26 @@ class LatentProductModel(object):
             # issue them on parallel streams, then the tiny dense part
             pre = m._out_prefix()
             sids = m.sampled_ids
-            if train:
+            early = os.environ.get('ARX_PLAN_EARLY', '0') == '1'
+
+            def plans():
                 irng = m.sets[pre].attr_range()
                 m.prefetch_plans({'user': [(m.sets['user'].attr_range(), m.u_indices['input'], POOL_MEAN)],
                                   pre: [(irng, sids, POOL_MEAN), (irng, item_ids, POOL_MEAN)]})
+            if train and early:
+                plans()
+            if train and not masks:
+                m.premake_dropout_mask((mb, self.size), keep_prob)
             (u0, _, urng), (Ps, bs, _), (Pt, bt, _) = m.pool_many([
                 ('user', m.u_indices['input'], POOL_MEAN, False, {}),
                 (pre, sids, POOL_MEAN, True, {}),
                 (pre, item_ids, POOL_MEAN, True, {})])
+            if train and not early:
+                # the backward plans depend on the ids only.  They are built on side streams UNDER THE DENSE
+                # MIDDLE of the step (which leaves most of each SM idle), not under the lookups: the lookup
+                # kernels need all four CTA slots of every SM to run as one balanced wave, and the
+                # latency-bound plan kernels (thousands of small CTAs) would take those slots.
+                plans()
             m._last_user = ('user', urng, m.u_indices['input'], POOL_MEAN)
             u = m.dropout(u0, keep_prob, masks[0] if masks else None)          # :78 / embed :236
             ctx = ('linear', m._last_user, keep_prob, getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None)
@@ -356,7 +369,7 @@ class LatentProductModel(object):
         self._g_users = users_dev.to(torch.int32).clone()
         self._g_items = items_dev.to(torch.int32).clone()
         self._g_loss_kind = loss
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(priority=-1)        # high priority: see EmbeddingAttribute.side_stream
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
@@ -364,7 +377,7 @@ class LatentProductModel(object):
         n0 = _lib.launch_count
         gs = self.global_step.eval()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph):
+        with torch.cuda.graph(self._graph, stream=side):
             self._g_loss = self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
         self._g_launches = _lib.launch_count - n0
         _lib.launch_count = n0                       # nothing ran during capture

@@ -301,7 +301,8 @@ int arx_scale_mask(const float* x, const float* mask, float scale, int64_t n, fl
                    void* stream);
 
 /* Launch-shape knobs for measurement sweeps (tools/bench_pool.py): "flat_epb" = 0 (auto) | 1..16 (entities per CTA
- * pass of the flat forward kernel), "apply_ctas_per_sm" = 1..4 (persistent grid of pool_bwd_apply).  No reference
+ * pass of the flat forward kernel), "apply_ctas_per_sm" = 1..4 (persistent grid of pool_bwd_apply), "plan_agg" = 0 | 1 (block-aggregated plan
+ * kernels; needs tables of < 2^27 rows).  No reference
  * counterpart; results are identical for every setting. */
 int arx_set_tuning(const char* key, int value);
 

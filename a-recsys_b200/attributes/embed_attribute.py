@@ -121,6 +121,10 @@ class EmbeddingAttribute(object):
         _lib.load()
         # shard = (G, r): this GPU stores rows t with t % G == r of every table
         self.shard = shard if (shard is not None and shard[0] > 1) else None
+        if self.shard is not None:
+            # the row-sharded (multi-GPU) step was validated with the warp-per-bag plan kernels; the block-aggregated
+            # ones are enabled for it once they have been measured at N > 1
+            _lib.load().arx_set_tuning(b'plan_agg', 0)
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.user_attributes = user_attributes
         self.item_attributes = item_attributes
@@ -790,7 +794,10 @@ class EmbeddingAttribute(object):
         if not hasattr(self, '_side_streams'):
             self._side_streams = {}
         if k not in self._side_streams:
-            self._side_streams[k] = torch.cuda.Stream(device=self.device, priority=0 if k >= 8 else -1)
+            # (single-GPU step only: the row-sharded step keeps default priorities — its NCCL exchanges are part
+            # of the captured graph and were validated at N = 2 / 4 with this scheduling)
+            prio = (0 if k >= 8 else -1) if self.shard is None else 0
+            self._side_streams[k] = torch.cuda.Stream(device=self.device, priority=prio)
         return self._side_streams[k]
 
     def pool_many(self, requests):

@@ -369,7 +369,9 @@ class LatentProductModel(object):
         self._g_users = users_dev.to(torch.int32).clone()
         self._g_items = items_dev.to(torch.int32).clone()
         self._g_loss_kind = loss
-        side = torch.cuda.Stream(priority=-1)        # high priority: see EmbeddingAttribute.side_stream
+        single = self.att_emb.shard is None
+        # high priority on one GPU (see EmbeddingAttribute.side_stream); default streams for the sharded step
+        side = torch.cuda.Stream(priority=-1) if single else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
@@ -377,7 +379,7 @@ class LatentProductModel(object):
         n0 = _lib.launch_count
         gs = self.global_step.eval()
         self._graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._graph, stream=side):
+        with (torch.cuda.graph(self._graph, stream=side) if single else torch.cuda.graph(self._graph)):
             self._g_loss = self.step(None, self._g_users, self._g_items, loss=loss, sync=False)
         self._g_launches = _lib.launch_count - n0
         _lib.launch_count = n0                       # nothing ran during capture

@@ -325,9 +325,6 @@ def main():
         t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_total, ms_e2e = float(t[0]), float(t[1])
-    if world > 1:
-        torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
     if rank != 0:
         return
     ms_step = ms_total / a.steps

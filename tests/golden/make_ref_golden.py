@@ -25,6 +25,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = os.environ.get('ARX_REFERENCE', '/root/reference')
+OUT = os.environ.get('ARX_GOLDEN_OUT', HERE)          # where the .npz fixtures are written (default: next to this script)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 sys.path.insert(0, os.path.join(ROOT, 'oracle', 'tf1_shim'))
@@ -188,7 +189,7 @@ def run_hmf_case(name, n_steps=6):
     out['recommend/indices'] = np.asarray(rec, dtype=np.int64)
     out['global_step'] = int(model.global_step.numpy())
     tf.set_dropout_hook(None)
-    path = os.path.join(HERE, 'ref_hmf_%s.npz' % name)
+    path = os.path.join(OUT, 'ref_hmf_%s.npz' % name)
     np.savez_compressed(path, **out)
     print('%-18s losses %s  eval %.6f  -> %s' % (name, np.round(losses, 5).tolist(), ev, os.path.basename(path)))
 
@@ -317,7 +318,7 @@ def run_lstm_case(name, n_steps=4):
     sess.run(model.dropoutAssign_op)
     out['global_step'] = int(model.global_step.numpy())
     tf.set_dropout_hook(None)
-    path = os.path.join(HERE, 'ref_lstm_%s.npz' % name)
+    path = os.path.join(OUT, 'ref_lstm_%s.npz' % name)
     np.savez_compressed(path, **out)
     print('lstm %-14s losses %s gnorm %s eval %.5f -> %s' % (name, np.round(losses, 4).tolist(),
                                                           np.round(norms, 3).tolist(), ev, os.path.basename(path)))
@@ -393,7 +394,7 @@ def run_cbow_case(name, n_steps=4):
     rec = model.step(sess, users.tolist(), [x.tolist() for x in ins], forward_only=True, recommend=True)
     out['recommend/indices'] = np.asarray(rec, dtype=np.int64)
     tf.set_dropout_hook(None)
-    path = os.path.join(HERE, 'ref_cbow_%s.npz' % name)
+    path = os.path.join(OUT, 'ref_cbow_%s.npz' % name)
     np.savez_compressed(path, **out)
     print('cbow %-16s losses %s eval %.5f -> %s' % (name, np.round(losses, 4).tolist(), ev, os.path.basename(path)))
 

@@ -326,3 +326,22 @@ def test_cuda_path_reproduces_reference_cbow_run(cuda, name, exact):
             assert np.array_equal(np.asarray(rec), c.d['recommend/indices'])
     finally:
         _lib.exact_fp32 = False
+
+
+# ------------------------------------------------------------------ provenance of the fixtures ------
+@pytest.mark.skipif(not os.path.isdir('/root/reference/hmf'), reason='reference sources only exist in the authoring container')
+@pytest.mark.parametrize('spec', ['mw_linear', 'rs_sig_exp', 'lstm:ce_adagrad_clipped', 'cbow:warp_sep_ni3'])
+def test_committed_fixture_regenerates_from_the_reference_sources(tmp_path, spec):
+    """The committed .npz really is what the unmodified reference code computes on the shim: regenerate it in a
+    fresh interpreter and compare every array."""
+    import subprocess
+    import sys
+    env = dict(os.environ, ARX_GOLDEN_OUT=str(tmp_path))
+    subprocess.check_call([sys.executable, os.path.join(GOLD, 'make_ref_golden.py'), spec], env=env,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    kind, name = spec.split(':') if ':' in spec else ('hmf', spec)
+    fn = 'ref_%s_%s.npz' % (kind, name)
+    new, old = np.load(os.path.join(str(tmp_path), fn)), np.load(os.path.join(GOLD, fn))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        assert np.array_equal(new[k], old[k]), k

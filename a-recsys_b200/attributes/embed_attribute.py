@@ -125,6 +125,10 @@ class EmbeddingAttribute(object):
             # the row-sharded (multi-GPU) step was validated with the warp-per-bag plan kernels; the block-aggregated
             # ones are enabled for it once they have been measured at N > 1
             _lib.load().arx_set_tuning(b'plan_agg', 0)
+        vmax = max(list(user_attributes._embedding_classes_list_cat) + list(user_attributes._embedding_classes_list_mulhot) +
+                   list(item_attributes._embedding_classes_list_cat) + list(item_attributes._embedding_classes_list_mulhot) + [0])
+        if vmax >= (1 << 27):      # the block-aggregated plan kernels key their hash on (attribute << 27) | row
+            _lib.load().arx_set_tuning(b'plan_agg', 0)
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.user_attributes = user_attributes
         self.item_attributes = item_attributes

@@ -7,7 +7,8 @@ on top of `oracle/tf1_shim` (a TF-1.0 op restatement) and records what that grap
     parameters after training, eval loss and top-k on the same inputs / weights / dropout masks;
   * gpu: the CUDA path through the C ABI must do the same (exact-fp32 contractions: 1e-4;
     tcgen05 tf32 contractions: the north star's 1e-3).
-Nothing here reads /root/reference at run time.
+Nothing here reads /root/reference at run time, except the provenance test at the end (skipped where the
+reference sources are absent), which regenerates fixtures from them and compares.
 """
 import glob
 import os

@@ -1,38 +1,41 @@
-"""Batch iterators of the LSTM runner (reference: lstm/data_iterator.py:6-42)."""
+"""Batch streams for the LSTM runner (same interface as the reference's lstm/data_iterator.py:6-42:
+`DataIterator(model, data_set, n_bucket, batch_size, train_buckets_scale)` with the generators
+`next_random()` and `next_sequence(stop, recommend)`), built on the model's own batch builders."""
 import numpy as np
 
 
 class DataIterator(object):
     def __init__(self, model, data_set, n_bucket, batch_size, train_buckets_scale):
-        self.data_set = data_set
-        self.n_bucket = n_bucket
-        self.batch_size = batch_size
+        self.model, self.data_set = model, data_set
+        self.n_bucket, self.batch_size = n_bucket, batch_size
         self.train_buckets_scale = train_buckets_scale
-        self.model = model
+        # cumulative share of the training sequences per bucket (only the random stream needs it)
+        self._cdf = None if train_buckets_scale is None else np.asarray(train_buckets_scale, dtype=np.float64)
+
+    def _draw_bucket(self):
+        """First bucket whose cumulative share exceeds one uniform draw: buckets are visited in proportion
+        to their size (lstm/data_iterator.py:14-18)."""
+        return int(np.searchsorted(self._cdf, np.random.random_sample(), side='right'))
 
     def next_random(self):
-        """bucket chosen with probability proportional to its size, batch drawn with replacement."""
+        """Endless training stream: a size-weighted random bucket, then a batch drawn with replacement."""
         while True:
-            r = np.random.random_sample()
-            bucket_id = min(i for i in range(len(self.train_buckets_scale)) if self.train_buckets_scale[i] > r)
-            users, inputs, outputs, weights, _ = self.model.get_batch(self.data_set, bucket_id)
-            yield users, inputs, outputs, weights, bucket_id
+            b = self._draw_bucket()
+            users, inputs, outputs, weights, _ = self.model.get_batch(self.data_set, b)
+            yield users, inputs, outputs, weights, b
 
     def next_sequence(self, stop=False, recommend=False):
-        bucket_id = 0
+        """Deterministic sweep: every bucket in order, consecutive windows of batch_size sequences until the
+        batch builder reports the bucket exhausted; one pass when `stop`, else round and round."""
+        fetch = self.model.get_batch_recommend if recommend else self.model.get_batch
         while True:
-            if bucket_id >= self.n_bucket:
-                if stop:
-                    break
-                bucket_id = 0
-            start_id = 0
-            while True:
-                fn = self.model.get_batch_recommend if recommend else self.model.get_batch
-                if len(self.data_set[bucket_id]) == 0:
-                    break
-                users, inputs, outputs, weights, finished = fn(self.data_set, bucket_id, start_id=start_id)
-                yield users, inputs, outputs, weights, bucket_id
-                if finished:
-                    break
-                start_id += self.batch_size
-            bucket_id += 1
+            for b in range(self.n_bucket):
+                if len(self.data_set[b]) == 0:
+                    continue
+                offset, exhausted = 0, False
+                while not exhausted:
+                    users, inputs, outputs, weights, exhausted = fetch(self.data_set, b, start_id=offset)
+                    yield users, inputs, outputs, weights, b
+                    offset += self.batch_size
+            if stop:
+                return

@@ -17,6 +17,8 @@ There is no CPU path: constructing this class without CUDA raises.
 import ctypes
 import math
 
+import os
+
 import numpy as np
 import torch
 
@@ -121,14 +123,15 @@ class EmbeddingAttribute(object):
         _lib.load()
         # shard = (G, r): this GPU stores rows t with t % G == r of every table
         self.shard = shard if (shard is not None and shard[0] > 1) else None
-        if self.shard is not None:
-            # the row-sharded (multi-GPU) step was validated with the warp-per-bag plan kernels; the block-aggregated
-            # ones are enabled for it once they have been measured at N > 1
-            _lib.load().arx_set_tuning(b'plan_agg', 0)
+        # Plan-kernel flavour (library-wide knob): block-aggregated by default; warp-per-bag for the row-sharded
+        # (multi-GPU) step, which was validated with those at N = 2 / 4 and gets the aggregated ones once they have
+        # been measured there, and for tables of >= 2^27 rows (the aggregated kernels key their hash on
+        # (attribute << 27) | row).  ARX_TUNE=plan_agg=.. still wins for A/B runs.
         vmax = max(list(user_attributes._embedding_classes_list_cat) + list(user_attributes._embedding_classes_list_mulhot) +
                    list(item_attributes._embedding_classes_list_cat) + list(item_attributes._embedding_classes_list_mulhot) + [0])
-        if vmax >= (1 << 27):      # the block-aggregated plan kernels key their hash on (attribute << 27) | row
-            _lib.load().arx_set_tuning(b'plan_agg', 0)
+        tune = dict(kv.split('=') for kv in os.environ.get('ARX_TUNE', '').split(',') if '=' in kv)
+        agg = 0 if (self.shard is not None or vmax >= (1 << 27)) else int(tune.get('plan_agg', 3))
+        _lib.load().arx_set_tuning(b'plan_agg', agg)
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.user_attributes = user_attributes
         self.item_attributes = item_attributes

@@ -194,6 +194,49 @@ def run_hmf_case(name, n_steps=6):
     print('%-18s losses %s  eval %.6f  -> %s' % (name, np.round(losses, 5).tolist(), ev, os.path.basename(path)))
 
 
+def run_hmf_warp_eval():
+    """loss_function='warp_eval' (hmf_model.py:123-124, embed_attribute.py:620-639): the per-row margin rank and
+    true rank the reference reports at evaluation time (keep_prob 1, dev positives)."""
+    import hmf_model as ref_hmf
+    dim, n_users, n_items, mb = 8, 60, 50, 16
+    ua, ia, i2l, l2i = small_dataset(n_users, n_items, 3, 25, 3, 7, 0, None, dim)
+    params = random_params(ua, ia, dim, 1)
+    V = len(l2i)
+    l2i_d = {int(v): int(l2i[v]) for v in range(V)}
+    i2l_d = {int(l2i[v]): int(v) for v in range(V)}
+    tf.reset_default_graph()
+    model = ref_hmf.LatentProductModel(n_users, n_items, dim, 1, mb, 0.3, 1.0, to_ref_attributes(ua, dim),
+                                       to_ref_attributes(ia, dim), i2l_d, l2i_d, loss_function='warp_eval',
+                                       dropout=0.5, top_N_items=10)
+    g = tf.get_default_graph()
+    for k, v in params.items():
+        g.by_name[k].load(v)
+    sess = tf.Session()
+    rng = np.random.default_rng(23)
+    users = rng.integers(0, n_users, mb)
+    items = rng.integers(0, V, mb)
+    users[:3] = users[3]
+    pos = positives(users, items, n_users, rng, n_items=V)
+    model.prepare_warp({}, pos)                        # forward_only reads pos_item_set_eval
+    margin, rank = model.step(sess, [int(u) for u in users], [int(i) for i in items], forward_only=True,
+                              loss='warp_eval')
+    out = {'dim': dim, 'n_users': n_users, 'n_items': n_items, 'mb': mb, 'l2i': np.asarray(l2i, dtype=np.int64),
+           'users': users.astype(np.int64), 'items': items.astype(np.int64),
+           'margin_rank': np.asarray(margin, dtype=np.float64), 'true_rank': np.asarray(rank, dtype=np.int64)}
+    pu = sorted(pos.keys())
+    out['pos_users'] = np.asarray(pu, dtype=np.int64)
+    out['pos_ptr'] = np.cumsum([0] + [len(pos[u]) for u in pu]).astype(np.int64)
+    out['pos_items'] = np.asarray([v for u in pu for v in pos[u]], dtype=np.int64)
+    pack_attributes('u_', ua, out)
+    pack_attributes('i_', ia, out)
+    for k, v in params.items():
+        out['init/' + k] = v
+    path = os.path.join(OUT, 'ref_hmfeval_warp_eval.npz')
+    np.savez_compressed(path, **out)
+    print('hmf warp_eval margin %s rank %s -> %s' % (np.round(margin[:4], 3).tolist(), np.asarray(rank)[:8].tolist(),
+                                                     os.path.basename(path)))
+
+
 LSTM_CASES = {
     # name: loss, use_concat, use_sep_item, withAdagrad, lr, max_gradient_norm   (lstm/run.py always passes
     # no_user_id=False)
@@ -401,9 +444,12 @@ def run_cbow_case(name, n_steps=4):
 
 def main():
     assert os.path.isdir(REF), 'reference sources not found at %s' % REF
-    names = sys.argv[1:] or (list(HMF_CASES) + ['lstm:' + n for n in LSTM_CASES] + ['cbow:' + n for n in CBOW_CASES])
+    names = sys.argv[1:] or (list(HMF_CASES) + ['hmfeval:warp_eval'] + ['lstm:' + n for n in LSTM_CASES] +
+                             ['cbow:' + n for n in CBOW_CASES])
     for n in names:
-        if n.startswith('lstm:'):
+        if n == 'hmfeval:warp_eval':
+            run_hmf_warp_eval()
+        elif n.startswith('lstm:'):
             run_lstm_case(n[5:])
         elif n.startswith('cbow:'):
             run_cbow_case(n[5:])

@@ -346,3 +346,30 @@ def test_committed_fixture_regenerates_from_the_reference_sources(tmp_path, spec
     assert sorted(new.files) == sorted(old.files)
     for k in old.files:
         assert np.array_equal(new[k], old[k]), k
+
+
+def test_oracle_reproduces_reference_warp_eval_ranks():
+    """loss 'warp_eval' (embed_attribute.py:620-639) as the reference's own graph reports it: per-row margin rank
+    (float) and true rank (integer, must be exact)."""
+    d = np.load(os.path.join(GOLD, 'ref_hmfeval_warp_eval.npz'))
+    dim, mb = int(d['dim']), int(d['mb'])
+    ua, ia = _attributes(d, 'u_', dim), _attributes(d, 'i_', dim)
+    l2i = d['l2i']
+    ia.set_target_prediction_from_map(l2i)
+    l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+    i2l_d = {int(l2i[v]): int(v) for v in range(len(l2i))}
+    params = {k[len('init/'):]: d[k] for k in d.files if k.startswith('init/')}
+    emb = O.OracleEmbeddingAttribute(ua, ia, mb, None, params, item_ind2logit_ind=i2l_d, logit_ind2item_ind=l2i_d,
+                                     dtype=np.float64)
+    om = O.OracleHMF(emb, loss='warp_eval', keep_prob=0.5, learning_rate=0.3)
+    pu, ptr, it = d['pos_users'], d['pos_ptr'], d['pos_items']
+    pos = {int(u): [int(v) for v in it[ptr[j]:ptr[j + 1]]] for j, u in enumerate(pu)}
+    emb.prepare_warp({}, pos)
+    users, items = d['users'].tolist(), d['items'].tolist()
+    u, _ = om.user_tower(users, 1.0, None)
+    logits = emb.get_prediction(u)
+    targets = np.asarray(emb.target_mapping([items])[0], dtype=np.int64)
+    mask = emb.build_mask(users, 'warp_eval', True)
+    margin, rank = O.compute_loss(logits, targets, 'warp_eval', mask)
+    np.testing.assert_allclose(margin, d['margin_rank'], rtol=2e-5, atol=1e-5)
+    assert np.array_equal(np.asarray(rank), d['true_rank'])

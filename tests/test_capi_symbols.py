@@ -47,3 +47,19 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 txt = open(os.path.join(d, f)).read()
                 assert 'import oracle' not in txt and 'from oracle' not in txt, f
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+    --impl reference legs may import it (the product path has no CPU fallback)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    offenders = []
+    for top in ('a-recsys_b200', 'hmf', 'lstm', 'word2vec', 'tools'):
+        for dp, _, files in os.walk(os.path.join(root, top)):
+            for f in files:
+                if f.endswith('.py'):
+                    src = open(os.path.join(dp, f), errors='replace').read()
+                    if re.search(r'^\s*(from|import)\s+oracle\b', src, re.M) or 'tf1_shim' in src:
+                        offenders.append(os.path.join(dp, f))
+    assert offenders == [], offenders

@@ -218,7 +218,7 @@ class TorchRefHMF(object):
                     continue
                 self.acc[k] += g * g
                 self.p[k] -= self.lr * g / torch.sqrt(self.acc[k])
-        return float(loss)
+        return float(loss.detach())
 
 
 class TorchRefSeq(TorchRefHMF):
@@ -329,6 +329,34 @@ class TorchRefSeq(TorchRefHMF):
             den = den + wt
         return (num / (den + 1e-12)).sum()
 
+    def topk_seq(self, users, item_inputs, k):
+        """Per-position top-k of softmax(full logits) (seqModel.py:514-519), keep_prob 1: int64 [T, mb, k];
+        ties -> lower index first (tf.nn.top_k)."""
+        T, mb = len(item_inputs), len(users)
+        with torch.no_grad():
+            if self.use_concat:
+                uproj = self._emb('user', self.ua, users, True, no_id=self.no_user_id) @ self.p['w_input_user']
+            else:
+                ue = self._emb('user', self.ua, users, False, no_id=self.no_user_id)
+            W, b, H = self.p['lstm_w'], self.p['lstm_b'], self.size
+            h = torch.zeros((mb, H), dtype=self.dtype)
+            c = torch.zeros((mb, H), dtype=self.dtype)
+            out = []
+            for t in range(T):
+                if self.use_concat:
+                    x = uproj + self._emb('item', self.ia, item_inputs[t], True,
+                                          no_attribute=self.no_input_item_feature) @ self.p['w_input_item']
+                else:
+                    ie = self._emb('item', self.ia, item_inputs[t], False, no_attribute=self.no_input_item_feature)
+                    x = torch.stack([ue, ie], 0).mean(0)
+                z = torch.cat([x, h], 1) @ W + b
+                i, j, f, o = torch.split(z, H, dim=1)
+                c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
+                h = torch.sigmoid(o) * torch.tanh(c)
+                prob = torch.softmax(self._pred(h, 'full'), 1)
+                out.append(torch.sort(prob, dim=1, descending=True, stable=True)[1][:, :k])
+            return torch.stack(out, 0).numpy()
+
     def step_seq(self, users, item_inputs, targets, weights, item_sampled=None, forward_only=False, masks=None):
         if item_sampled is not None and self.loss == 'mw':
             self.pass_sampled_items(item_sampled)
@@ -364,7 +392,7 @@ class TorchRefSeq(TorchRefHMF):
                     v -= self.lr * g / torch.sqrt(self.acc[k])
                 else:
                     v -= self.lr * g
-        return float(loss)
+        return float(loss.detach())
 
 
 class TorchRefCbow(TorchRefSeq):
@@ -411,4 +439,4 @@ class TorchRefCbow(TorchRefSeq):
                     continue
                 self.acc[k] += v.grad * v.grad
                 v -= self.lr * v.grad / torch.sqrt(self.acc[k])
-        return float(loss)
+        return float(loss.detach())

@@ -200,6 +200,9 @@ def test_oracle_reproduces_reference_lstm_run(name):
     ev = ref.step_seq(users, inp, tgt, w, forward_only=True)
     want = float(c.d['eval/loss'])
     assert abs(ev - want) <= 2e-5 * max(1.0, abs(want)), (ev, want)
+    # per-position top-k of softmax(logits) (seqModel.py:514-519) on the same eval batch
+    tk = ref.topk_seq(users, inp, c.topk)
+    assert np.array_equal(tk, c.d['eval/topk_indexes'])
 
 
 @pytest.mark.gpu

@@ -403,6 +403,19 @@ class TorchRefCbow(TorchRefSeq):
         super(TorchRefCbow, self).__init__(*a, **kw)
         self.ni = ni
 
+    def recommend(self, users, item_inputs, k):
+        """top-k logit indices of logits_test (cbow_model.py:95-104,138-139): no dropout, user embedding alone
+        when n_input_items == 0; ties -> lower index first."""
+        n_input = max(self.ni, 1)
+        with torch.no_grad():
+            ue = self._emb('user', self.ua, users, False)
+            if self.ni == 0:
+                x = ue
+            else:
+                its = torch.stack([self._emb('item', self.ia, item_inputs[j], False) for j in range(n_input)], 0).mean(0)
+                x = torch.stack([ue, its], 0).mean(0)
+            return torch.sort(self._pred(x, 'full'), dim=1, descending=True, stable=True)[1][:, :k].numpy()
+
     def step_cbow(self, users, item_inputs, item_outputs, item_sampled=None, forward_only=False, mask=None):
         if item_sampled is not None and self.loss == 'mw':
             self.pass_sampled_items(item_sampled)

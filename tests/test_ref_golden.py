@@ -296,6 +296,7 @@ def test_oracle_reproduces_reference_cbow_run(name):
     ev = ref.step_cbow(users, ins, outs, forward_only=True)
     want = float(c.d['eval/loss'])
     assert abs(ev - want) <= 2e-5 * max(1.0, abs(want)), (ev, want)
+    assert np.array_equal(ref.recommend(users, ins, c.top_n), c.d['recommend/indices'])
 
 
 @pytest.mark.gpu

@@ -1,0 +1,146 @@
+"""Host-side logic against the reference's OWN pure-Python functions (no TensorFlow involved): ranking metrics,
+frequency / positives preparation, and the batch builders of the three models under identical RNG seeds.
+These import /root/reference directly and therefore only run in the authoring container (skipped elsewhere);
+nothing is copied from the reference."""
+import builtins
+import importlib.util
+import os
+import random
+import sys
+import types
+
+import numpy as np
+import pytest
+
+import arecsys_b200  # noqa: F401
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'utils')),
+                                reason='reference sources only exist in the authoring container')
+SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'tf1_shim')
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture()
+def py2():
+    """python-2 builtins the reference uses without six"""
+    had = hasattr(builtins, 'xrange')
+    builtins.xrange = range
+    yield
+    if not had:
+        del builtins.xrange
+
+
+def test_ranking_metrics_match_reference(py2):
+    ref = _load(os.path.join(REF, 'utils', 'eval_metrics.py'), 'ref_eval_metrics')
+    from arecsys_b200.utils import evaluate as ours
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n_items = int(rng.integers(40, 200))
+        n_rec = int(rng.integers(3, 31))                    # also lists shorter than the largest N
+        X = {u: rng.permutation(n_items)[:n_rec].tolist() for u in range(7)}                 # recommendations
+        T = {u: rng.permutation(n_items)[:int(rng.integers(1, 40))].tolist() for u in range(9)}   # users 7, 8: no recs
+        want = ref.metrics(X, T)
+        got = ours.metrics(X, T)
+        assert sorted(want) == sorted(got)
+        for m in want:
+            np.testing.assert_allclose(np.asarray(got[m], dtype=np.float64), np.asarray(want[m], dtype=np.float64),
+                                       rtol=1e-12, err_msg=m)
+
+
+def test_item_frequency_and_positive_items_match_reference(py2):
+    ref = _load(os.path.join(REF, 'utils', 'prepare_train.py'), 'ref_prepare_train')
+    from arecsys_b200.utils import prepare_train as ours
+    rng = np.random.default_rng(1)
+    data_tr = [(int(u), int(i), 0) for u, i in zip(rng.integers(0, 30, 400), rng.zipf(1.5, 400) % 25)]
+    data_va = [(int(u), int(i), 0) for u, i in zip(rng.integers(0, 30, 100), rng.integers(0, 25, 100))]
+    for power in (0.0, 0.5, 1.0):
+        ri, rp = ref.item_frequency(data_tr, power)
+        oi, op = ours.item_frequency(data_tr, power)
+        assert list(ri) == list(oi)
+        np.testing.assert_allclose(np.asarray(op, dtype=np.float64), np.asarray(rp, dtype=np.float64), rtol=1e-12)
+    rt, rv = ref.positive_items(data_tr, data_va)
+    ot, ov = ours.positive_items(data_tr, data_va)
+    assert {k: sorted(v) for k, v in rt.items()} == {k: sorted(v) for k, v in ot.items()}
+    assert {k: sorted(v) for k, v in rv.items()} == {k: sorted(v) for k, v in ov.items()}
+    # host sampler: same numpy stream -> same pool (the device sampler is a different, equivalent-in-law generator)
+    np.random.seed(5)
+    a = ref.sample_items(ri, 10, rp)
+    np.random.seed(5)
+    b = ours.sample_items(oi, 10, op)
+    assert list(a[0]) == list(b[0]) and a[1] == b[1]
+
+
+@pytest.fixture()
+def ref_models(py2):
+    """the reference model classes, imported on the TF shim (only their pure-Python batch builders are used)"""
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k == 'tensorflow' or k.startswith('tensorflow.')}
+    for k in saved_mods:
+        del sys.modules[k]
+    sys.path.insert(0, SHIM)
+    for sub in ('attributes', 'hmf', 'lstm', 'word2vec', 'utils'):
+        sys.path.append(os.path.join(REF, sub))
+    for m in ('hmf_model', 'seqModel', 'embed_attribute', 'mulhot_index', 'data_iterator'):
+        sys.modules.pop(m, None)
+    import hmf_model
+    import seqModel
+    yield hmf_model, seqModel
+    sys.path[:] = saved_path
+    for k in [k for k in sys.modules if k == 'tensorflow' or k.startswith('tensorflow.')]:
+        del sys.modules[k]
+    sys.modules.update(saved_mods)
+    for m in ('hmf_model', 'seqModel', 'embed_attribute', 'mulhot_index', 'data_iterator'):
+        sys.modules.pop(m, None)
+
+
+def test_hmf_batch_builders_match_reference(ref_models):
+    ref_hmf, _ = ref_models
+    from arecsys_b200.hmf.hmf_model import LatentProductModel as Ours
+    data = [(u, i, 0) for u in range(11) for i in range(u % 4 + 1)]
+    for cls_a, cls_b in ((ref_hmf.LatentProductModel, Ours),):
+        fa = types.SimpleNamespace(batch_size=8, data_length=None, train_permutation=None, start_index=None)
+        fb = types.SimpleNamespace(batch_size=8, data_length=None, train_permutation=None, start_index=None)
+        random.seed(3)
+        a = [cls_a.get_batch(fa, data) for _ in range(5)]
+        random.seed(3)
+        b = [cls_b.get_batch(fb, data) for _ in range(5)]
+        assert [(list(x[0]), list(x[1])) for x in a] == [(list(x[0]), list(x[1])) for x in b]
+        np.random.seed(4)
+        a = [cls_a.get_permuted_batch(fa, data) for _ in range(9)]          # wraps around (restart rule :249-251)
+        np.random.seed(4)
+        b = [cls_b.get_permuted_batch(fb, data) for _ in range(9)]
+        assert [(list(x[0]), list(x[1])) for x in a] == [(list(x[0]), list(x[1])) for x in b]
+
+
+def test_lstm_batch_builder_matches_reference(ref_models):
+    _, ref_seq = ref_models
+    from arecsys_b200.lstm.seqModel import SeqModel as Ours
+    rng = np.random.default_rng(7)
+    buckets = [3, 6]
+    data_set = [[(int(rng.integers(0, 9)), rng.integers(2, 20, int(rng.integers(1, 4))).tolist()) for _ in range(7)],
+                [(int(rng.integers(0, 9)), rng.integers(2, 20, int(rng.integers(4, 7))).tolist()) for _ in range(10)]]
+
+    def fake():
+        return types.SimpleNamespace(buckets=buckets, batch_size=4, START_ID=1, PAD_ID=1, USER_PAD_ID=0)
+    for bucket in (0, 1):
+        fa, fb = fake(), fake()
+        fb._batch_major = lambda l: Ours._batch_major(fb, l)
+        random.seed(11)
+        a = ref_seq.SeqModel.get_batch(fa, data_set, bucket)
+        random.seed(11)
+        b = Ours.get_batch(fb, data_set, bucket)
+        for x, y in zip(a[:4], b[:4]):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+        for start in (0, 4, 8):                                              # sequential sweep incl. the padded tail
+            a = ref_seq.SeqModel.get_batch(fa, data_set, bucket, start_id=start)
+            b = Ours.get_batch(fb, data_set, bucket, start_id=start)
+            for x, y in zip(a[:4], b[:4]):
+                assert np.array_equal(np.asarray(x), np.asarray(y))
+            assert bool(a[4]) == bool(b[4])

@@ -144,3 +144,60 @@ def test_lstm_batch_builder_matches_reference(ref_models):
             for x, y in zip(a[:4], b[:4]):
                 assert np.array_equal(np.asarray(x), np.asarray(y))
             assert bool(a[4]) == bool(b[4])
+
+
+def test_evaluation_class_matches_reference_on_ml1m(tmp_path, py2):
+    """utils/evaluate.py::Evaluation on a copy of the bundled MovieLens-1m files: the eval files it writes
+    (res_T.csv, historical_train.csv ...), the user order, and the P/R/MAP/NDCG scores of a random recommendation with
+    and without history exclusion — reference class vs ours."""
+    import shutil
+    import pandas as pd
+    src = os.path.join(REF, 'examples', 'dataset')
+    dirs = []
+    for tag in ('ref', 'ours'):
+        d = str(tmp_path / tag)
+        os.makedirs(d)
+        for f in os.listdir(src):
+            if f.endswith('.csv'):
+                shutil.copy(os.path.join(src, f), os.path.join(d, f))
+                os.chmod(os.path.join(d, f), 0o644)
+        dirs.append(d)
+    saved_path = list(sys.path)
+    sys.path.insert(0, os.path.join(REF, 'utils'))
+    for m in ('evaluate', 'eval_metrics', 'submit', 'load_data', 'pandatools'):
+        sys.modules.pop(m, None)
+    try:
+        import load_data as ref_load
+
+        class PdProxy(object):                              # python 2 read the Latin-1 bytes of i.csv as-is
+            def __getattr__(self, k):
+                return getattr(pd, k)
+
+            def read_csv(self, *a, **k):
+                k.setdefault('encoding', 'latin-1')
+                return pd.read_csv(*a, **k)
+        ref_load.pd = PdProxy()
+        import evaluate as ref_eval
+        ref = ref_eval.Evaluation(dirs[0] + '/')
+        from arecsys_b200.utils.evaluate import Evaluation
+        ours = Evaluation(dirs[1] + '/')
+        for f in ('res_T.csv', 'res_T_test.csv', 'historical_train.csv', 'historical_train_test.csv'):
+            a = pd.read_csv(os.path.join(dirs[0], f), sep=None, engine='python').sort_values('user_id').reset_index(drop=True)
+            b = pd.read_csv(os.path.join(dirs[1], f), sep=None, engine='python').sort_values('user_id').reset_index(drop=True)
+            assert a.equals(b), f
+        assert ref.get_user_n() == ours.get_user_n()
+        assert sorted(ref.get_uinds()) == sorted(ours.get_uinds())
+        rng = np.random.default_rng(0)
+        n_items = len(ref.Iid2ind)
+        item_ids = np.asarray(list(ref.Iid2ind.keys()))
+        uids = ref.get_uids()
+        rec_a = {u: item_ids[rng.permutation(n_items)[:30]].tolist() for u in uids}
+        rec_b = {u: list(v) for u, v in rec_a.items()}
+        ref.eval_on(rec_a)
+        ours.eval_on(rec_b)
+        for x, y in zip(ref.get_scores(), ours.get_scores()):
+            np.testing.assert_allclose(np.asarray(y, dtype=np.float64), np.asarray(x, dtype=np.float64), rtol=1e-12)
+    finally:
+        sys.path[:] = saved_path
+        for m in ('evaluate', 'eval_metrics', 'submit', 'load_data', 'pandatools'):
+            sys.modules.pop(m, None)

@@ -201,3 +201,36 @@ def test_evaluation_class_matches_reference_on_ml1m(tmp_path, py2):
         sys.path[:] = saved_path
         for m in ('evaluate', 'eval_metrics', 'submit', 'load_data', 'pandatools'):
             sys.modules.pop(m, None)
+
+
+def test_cbow_window_batcher_targets_match_reference(py2):
+    """word2vec/data_iterator.py::get_next_cbow vs the vectorised batcher: the (user, target) stream is deterministic
+    and must be identical batch by batch; the drawn inputs are random in both, so they are held to the window they
+    must come from and to the with/without-replacement rule."""
+    ref = _load(os.path.join(REF, 'word2vec', 'data_iterator.py'), 'ref_w2v_iter')
+    from arecsys_b200.word2vec.data_iterator import DataIterator as Ours
+    rng = np.random.default_rng(2)
+    PAD = 999
+    seq = []
+    for u in range(23):
+        seq.append((u, PAD))
+        seq.extend((u, int(v)) for v in rng.integers(0, 500, int(rng.integers(1, 9))))
+    for mb, ni, window in ((8, 2, 3), (16, 3, 5), (5, 1, 1)):
+        np.random.seed(0)
+        a = ref.DataIterator(seq, PAD, mb, ni, window, False).get_next_cbow()
+        b = Ours(seq, PAD, mb, ni, window, False).get_next_cbow()
+        items = np.asarray([s[1] for s in seq])
+        pos_of = {}
+        for p, (u, i) in enumerate(seq):
+            pos_of.setdefault((u, i), []).append(p)
+        for step in range(40):                                   # several sweeps over the 23-user stream
+            ua, ia, oa = next(a)
+            ub, ib, ob = next(b)
+            assert np.array_equal(np.asarray(ua), np.asarray(ub)), (mb, ni, window, step)
+            assert np.array_equal(np.asarray(oa), np.asarray(ob)), (mb, ni, window, step)
+            assert len(ia) == len(ib) == ni
+            for k in range(mb):
+                wins = [set(items[(p - window + np.arange(window)) % len(seq)].tolist()) for p in pos_of[(int(ub[k]), int(ob[k]))]]
+                for src in (ia, ib):
+                    drawn = [int(src[j][k]) for j in range(ni)]
+                    assert any(all(d in w for d in drawn) for w in wins), (drawn, wins)

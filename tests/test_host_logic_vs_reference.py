@@ -144,6 +144,10 @@ def test_lstm_batch_builder_matches_reference(ref_models):
             for x, y in zip(a[:4], b[:4]):
                 assert np.array_equal(np.asarray(x), np.asarray(y))
             assert bool(a[4]) == bool(b[4])
+            ra = ref_seq.SeqModel.get_batch_recommend(fa, data_set, bucket, start_id=start)      # :407-451
+            rb = Ours.get_batch_recommend(fb, data_set, bucket, start_id=start)
+            assert list(ra[0]) == list(rb[0]) and list(ra[2]) == list(rb[2]) and list(ra[3]) == list(rb[3])
+            assert np.array_equal(np.asarray(ra[1]), np.asarray(rb[1])) and bool(ra[4]) == bool(rb[4])
 
 
 def test_evaluation_class_matches_reference_on_ml1m(tmp_path, py2):

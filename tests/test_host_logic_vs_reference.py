@@ -238,3 +238,61 @@ def test_cbow_window_batcher_targets_match_reference(py2):
                 for src in (ia, ib):
                     drawn = [int(src[j][k]) for j in range(ni)]
                     assert any(all(d in w for d in drawn) for w in wins), (drawn, wins)
+
+
+def _functions(path, names, extra=None):
+    """Compile selected top-level functions of a runner file in isolation (the runner modules define their flag
+    surface at import time, which needs TensorFlow's tf.app.flags in the reference)."""
+    import ast
+    tree = ast.parse(open(path, encoding='latin-1').read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert sorted(n.name for n in keep) == sorted(names), (path, [n.name for n in keep])
+    for n in keep:                                       # defaults like FLAGS.x are evaluated at definition time
+        n.args.defaults = [d if not any(isinstance(x, ast.Name) and x.id == 'FLAGS' for x in ast.walk(d))
+                           else ast.Constant(value=None) for d in n.args.defaults]
+    ns = {'np': np, 'random': random, 'xrange': range}
+    ns.update(extra or {})
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, 'exec'), ns)
+    return ns
+
+
+def test_lstm_runner_sequence_helpers_match_reference(py2):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ['split_buckets', 'get_buckets_id', 'form_sequence_prediction', 'form_sequence', 'split_train_dev']
+    flags = types.SimpleNamespace(seed=0)
+    ref = _functions(os.path.join(REF, 'lstm', 'run.py'), names, {'FLAGS': flags})
+    ours = _functions(os.path.join(root, 'lstm', 'run.py'), names, {'FLAGS': flags})
+    rng = np.random.default_rng(4)
+    data = [(int(u), int(i), int(w)) for u, i, w in zip(rng.integers(0, 12, 900), rng.integers(0, 60, 900),
+                                                        rng.integers(0, 50, 900))]
+    for maxlen in (5, 20, 100):
+        a, b = ref['form_sequence'](data, maxlen), ours['form_sequence'](data, maxlen)
+        assert sorted(map(repr, a)) == sorted(map(repr, b)), maxlen       # user order = dict order in both
+    seqs = ref['form_sequence'](data, 20)
+    buckets = [5, 10, 20]
+    assert ref['split_buckets'](seqs, buckets) == ours['split_buckets'](seqs, buckets)
+    assert [ref['get_buckets_id'](l, buckets) for l in range(0, 25)] == [ours['get_buckets_id'](l, buckets) for l in range(0, 25)]
+    uids = list(range(0, 15))
+    assert ref['form_sequence_prediction'](seqs, uids, 8, 77) == ours['form_sequence_prediction'](seqs, uids, 8, 77)
+    assert ref['split_train_dev'](seqs, 0.3) == ours['split_train_dev'](seqs, 0.3)
+
+
+def test_w2v_runner_sequence_helpers_match_reference(py2):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = ['get_user_items_seq', 'form_train_seq', 'prepare_valid']
+    flags = types.SimpleNamespace(after40=False)
+    extra = {'FLAGS': flags, 'to_week': lambda t: t // (7 * 24 * 3600)}
+    ref = _functions(os.path.join(REF, 'word2vec', 'run_w2v.py'), names, extra)
+    ours = _functions(os.path.join(root, 'word2vec', 'run_w2v.py'), names, extra)
+    rng = np.random.default_rng(6)
+    data_tr = [(int(u), int(i), int(t)) for u, i, t in zip(rng.integers(0, 9, 300), rng.integers(0, 40, 300),
+                                                          rng.integers(0, 1000, 300))]
+    data_va = [(int(u), int(i), int(t)) for u, i, t in zip(rng.integers(0, 11, 60), rng.integers(0, 40, 60),
+                                                          rng.integers(1000, 2000, 60))]
+    a, b = ref['get_user_items_seq'](data_tr), ours['get_user_items_seq'](data_tr)
+    assert {k: list(v) for k, v in a.items()} == {k: list(v) for k, v in b.items()}
+    for opt in (0, 1):
+        assert list(map(tuple, ref['form_train_seq'](a, 999, opt))) == list(map(tuple, ours['form_train_seq'](b, 999, opt)))
+    for n in (0, 2, 3):
+        ra, rb = ref['prepare_valid'](data_va, a, 999, n), ours['prepare_valid'](data_va, b, 999, n)
+        assert repr(ra) == repr(rb), n

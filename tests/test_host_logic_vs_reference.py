@@ -296,3 +296,70 @@ def test_w2v_runner_sequence_helpers_match_reference(py2):
     for n in (0, 2, 3):
         ra, rb = ref['prepare_valid'](data_va, a, 999, n), ours['prepare_valid'](data_va, b, 999, n)
         assert repr(ra) == repr(rb), n
+
+
+def test_attribute_store_builders_match_reference(tmp_path, py2):
+    """SURVEY 8(a) a1 — the arrays the CUDA path gathers from: utils/preprocess.py::tokenize_attribute_map,
+    filter_cat and filter_mulhot of the reference (run on the shim's text-mode gfile, vocabulary files given)
+    against this repo's tokenize_attribute_map and Attributes.set_target_prediction_from_map."""
+    import pickle
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k == 'tensorflow' or k.startswith('tensorflow.')}
+    for k in saved_mods:
+        del sys.modules[k]
+    sys.modules['cPickle'] = pickle
+    sys.path.insert(0, SHIM)
+    sys.modules.pop('preprocess', None)
+    try:
+        ref = _load(os.path.join(REF, 'utils', 'preprocess.py'), 'ref_preprocess')
+        from arecsys_b200.utils import preprocess as ours
+        from arecsys_b200.attributes.attribute import Attributes
+        rng = np.random.default_rng(9)
+        N = 57
+        genres = ['g%d' % k for k in range(9)]
+        words = ['w%d' % k for k in range(40)]
+        feats = np.empty((N, 4), dtype=object)
+        for n in range(N):
+            feats[n, 0] = 'id%d' % n
+            feats[n, 1] = int(rng.integers(0, 5))                                           # categorical, numeric
+            feats[n, 2] = ','.join(rng.choice(genres, int(rng.integers(1, 4)), replace=False))
+            feats[n, 3] = ','.join(rng.choice(words, int(rng.integers(1, 8)), replace=True)) if n % 11 else 'zzz'   # all-UNK bag
+        types_ = [0, 0, 1, 1]
+        d = str(tmp_path)
+        vocabs = [['_UNK', '_START'] + ['id%d' % n for n in range(0, N, 2)],               # half the ids are UNK
+                  ['_UNK', '_START', '0', '1', '2', '3'],                                  # value 4 is UNK
+                  ['_UNK', '_START'] + genres[:7],
+                  ['_UNK', '_START'] + words[:25]]
+        for i, v in enumerate(vocabs):
+            with open(os.path.join(d, 'item_vocab%d_%d' % (i, 50000)), 'w') as f:
+                f.write('\n'.join(v) + '\n')
+        a = ref.tokenize_attribute_map(d, feats.copy(), types_, 50000, 50000, 'item')
+        b = ours.tokenize_attribute_map(d, feats.copy(), types_, 50000, 50000, 'item')
+        assert list(a[7]) == [len(vocabs[0]), len(vocabs[1])] and list(a[8]) == [len(vocabs[2]), len(vocabs[3])]
+        assert len(set(np.asarray(a[3][1]).tolist())) > 10          # the vocabulary really is in use
+        assert a[0] == b[0] and a[2] == b[2] and list(a[4]) == list(b[4]) and list(a[7]) == list(b[7]) and list(a[8]) == list(b[8])
+        for x, y in zip(a[1], b[1]):
+            assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64))       # features_cat
+        for k in (3, 5, 6):                                                                            # values, starts, lengths
+            for x, y in zip(a[k], b[k]):
+                assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64)), k
+        # catalog-ordered copies for a partial catalog
+        l2i = {v: int(it) for v, it in enumerate(rng.permutation(N)[:31])}
+        cat_tr = ref.filter_cat(a[0], a[1], l2i)
+        (_, vals_tr, _, _, seg_tr, len_tr) = ref.filter_mulhot(d, feats.copy(), types_, 50000, l2i, 'item')
+        att = Attributes(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8])
+        att.set_target_prediction_from_map(l2i)
+        for x, y in zip(cat_tr, att.full_cat_tr):
+            assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64))
+        for x, y in zip(vals_tr, att.full_values_tr):
+            assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64))
+        for x, y in zip(seg_tr, att.full_segids_tr):
+            assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64))
+        for x, y in zip(len_tr, att.full_lengths_tr):
+            np.testing.assert_allclose(np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64))
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == 'tensorflow' or k.startswith('tensorflow.')]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        sys.modules.pop('cPickle', None)

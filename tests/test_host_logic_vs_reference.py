@@ -363,3 +363,66 @@ def test_attribute_store_builders_match_reference(tmp_path, py2):
             del sys.modules[k]
         sys.modules.update(saved_mods)
         sys.modules.pop('cPickle', None)
+
+
+@pytest.mark.parametrize('comb,logits', [('mix', 3100), ('het', 3100)])
+def test_het_mix_pipeline_matches_reference_on_ml1m(tmp_path, py2, comb, logits):
+    """attributes/comb_attribute.py (MIX.mix_attr, HET / MIX index_mapping, Comb_Attributes.get_attributes) of the
+    reference, run end to end on the bundled MovieLens-1m files, against this repo's classes.  Only the vocabulary
+    creation step (Python-2-only code whose ordering is Python-2 dict order) is substituted, in BOTH pipelines, by
+    this repo's create_dictionary / create_dictionary_mix; everything downstream — attribute mixing, tokenisation,
+    frequency-ordered logit map, catalog filters — is the reference's own code."""
+    import copy
+    import pickle
+    saved_path = list(sys.path)
+    saved_mods = {k: v for k, v in sys.modules.items() if k == 'tensorflow' or k.startswith('tensorflow.')}
+    for k in saved_mods:
+        del sys.modules[k]
+    sys.modules['cPickle'] = pickle
+    sys.path.insert(0, SHIM)
+    sys.path.insert(0, os.path.join(REF, 'utils'))
+    sys.path.insert(0, os.path.join(REF, 'attributes'))
+    for m in ('preprocess', 'comb_attribute', 'attribute'):
+        sys.modules.pop(m, None)
+    try:
+        import comb_attribute as ref_comb
+        from arecsys_b200.attributes import comb_attribute as our_comb
+        from arecsys_b200.utils import preprocess as our_pre
+        from arecsys_b200.utils.load_data import load_raw_data
+        (users, items, data_tr, data_va, user_features, item_features, user_index, item_index) = load_raw_data(
+            data_dir=os.path.join(REF, 'examples', 'dataset') + '/', _submit=0)
+        outs = []
+        for tag, mod in (('ref', ref_comb), ('ours', our_comb)):
+            d = str(tmp_path / tag) + '/'
+            os.makedirs(d)
+            u, i = np.copy(users), np.copy(items)
+            uf, itf = copy.deepcopy(user_features), copy.deepcopy(item_features)
+            if comb == 'mix':
+                c = mod.MIX(data_dir=d, logits_size_tr=logits, threshold=2)
+                c.create_dictionary = our_pre.create_dictionary_mix
+                u, i, uf, itf = c.mix_attr(u, i, uf, itf)
+            else:
+                c = mod.HET(data_dir=d, logits_size_tr=logits, threshold=2)
+                c.create_dictionary = our_pre.create_dictionary
+            outs.append(c.get_attributes(u, i, data_tr, uf, itf))
+        (ua, ia, i2l, l2i), (ub, ib, i2l_b, l2i_b) = outs
+        assert dict(i2l) == dict(i2l_b) and dict(l2i) == dict(l2i_b) and len(l2i) == logits
+        for a, b in ((ua, ub), (ia, ib)):
+            assert a.num_features_cat == b.num_features_cat and a.num_features_mulhot == b.num_features_mulhot
+            assert list(a._embedding_classes_list_cat) == list(b._embedding_classes_list_cat)
+            assert list(a._embedding_classes_list_mulhot) == list(b._embedding_classes_list_mulhot)
+            for name in ('features_cat', 'features_mulhot', 'mulhot_starts', 'mulhot_lengths'):
+                for x, y in zip(getattr(a, name), getattr(b, name)):
+                    assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64)), name
+        for name in ('full_cat_tr', 'full_values_tr', 'full_segids_tr'):
+            for x, y in zip(getattr(ia, name), getattr(ib, name)):
+                assert np.array_equal(np.asarray(x, dtype=np.int64), np.asarray(y, dtype=np.int64)), name
+        for x, y in zip(ia.full_lengths_tr, ib.full_lengths_tr):
+            np.testing.assert_allclose(np.asarray(x, dtype=np.float64).ravel(), np.asarray(y, dtype=np.float64).ravel())
+    finally:
+        sys.path[:] = saved_path
+        for k in [k for k in sys.modules if k == 'tensorflow' or k.startswith('tensorflow.')]:
+            del sys.modules[k]
+        sys.modules.update(saved_mods)
+        for m in ('preprocess', 'comb_attribute', 'attribute', 'cPickle'):
+            sys.modules.pop(m, None)

@@ -228,8 +228,9 @@ class TorchRefSeq(TorchRefHMF):
     params additionally hold 'lstm_w' [d_in+H, 4H], 'lstm_b' [4H] (+ 'w_input_user'/'w_input_item')."""
 
     def __init__(self, *a, size=8, use_concat=False, no_user_id=False, no_input_item_feature=False,
-                 max_gradient_norm=5.0, withAdagrad=True, item_output=False, **kw):
+                 max_gradient_norm=5.0, withAdagrad=True, item_output=False, output_feat=1, **kw):
         super(TorchRefSeq, self).__init__(*a, **kw)
+        self.output_feat = output_feat          # 0: score with the id table only (embed_attribute.py:164-165)
         self.size, self.use_concat, self.no_user_id = size, use_concat, no_user_id
         self.no_input_item_feature = no_input_item_feature
         self.clip, self.withAdagrad, self.item_output = max_gradient_norm, withAdagrad, item_output
@@ -272,10 +273,16 @@ class TorchRefSeq(TorchRefHMF):
         cat, val, seg, leng = self.full if pool == 'full' else self.sampled
         V = self.V if pool == 'full' else self.n_sampled
         innerps = []
-        for i in range(ia.num_features_cat):
+        n1 = 1 if self.output_feat == 0 else ia.num_features_cat
+        n2 = 0 if self.output_feat == 0 else ia.num_features_mulhot
+        if not hasattr(self, '_pred_tables'):
+            self._pred_tables = set()        # tables that feed the scoring matmul: TF holds their gradient dense
+        self._pred_tables.update(['%sembed_cat_%d' % (pre, i) for i in range(n1)] +
+                                 ['%sembed_mulhot_%d' % (pre, i) for i in range(n2)])
+        for i in range(n1):
             innerp = self.p['%sembed_cat_%d' % (pre, i)] @ u.t() + self.p['%s_bias_cat_%d' % (pre, i)]
             innerps.append(innerp.index_select(0, cat[i]))
-        for i in range(ia.num_features_mulhot):
+        for i in range(n2):
             innerp = self.p['%sembed_mulhot_%d' % (pre, i)] @ u.t() + self.p['%s_bias_mulhot_%d' % (pre, i)]
             innerps.append(seg_sum(innerp.index_select(0, val[i]), seg[i], V) / leng[i])
         return torch.stack(innerps, 0).mean(0).t()
@@ -370,7 +377,7 @@ class TorchRefSeq(TorchRefHMF):
         pre = 'item_output' if self.item_output else 'item'
         # tables reached ONLY through lookups keep IndexedSlices gradients: their norm is taken over
         # the un-merged slice values; every other gradient is dense
-        sparse_only = set(n for n, _ in self.slices if not n.startswith(pre + 'embed'))
+        sparse_only = set(n for n, _ in self.slices if n not in getattr(self, '_pred_tables', ()))
         sumsq = 0.0
         for k, v in self.p.items():
             if v.grad is None or k in sparse_only:

@@ -250,12 +250,25 @@ LSTM_CASES = {
     'ce_sgd_clipped': ('ce', False, False, False, 2.0, 0.5),        # norm > max_gradient_norm: clipping active
     'ce_adagrad_clipped': ('ce', False, True, True, 0.5, 0.25),
 }
+# non-default flags, fixtures named ref_lstmx_*: (loss, use_concat, sep, adagrad, lr, clip, extra kwargs)
+LSTMX_CASES = {
+    'ce_outfeat0': ('ce', False, False, True, 0.5, 5.0, {'output_feat': 0}),
+    'ce_outfeat0_sep': ('ce', True, True, True, 0.5, 5.0, {'output_feat': 0}),
+    'ce_noitemfeat': ('ce', False, False, True, 0.5, 5.0, {'no_input_item_feature': True}),
+    # (use_concat + no_input_item_feature is not usable in the reference: w_input_item keeps the full concat width,
+    #  seqModel.py:135-137 vs embed_attribute.py:368-369)
+    'warp_noitemfeat': ('warp', False, False, True, 0.5, 5.0, {'no_input_item_feature': True}),
+}
 
 
-def run_lstm_case(name, n_steps=4):
+def run_lstm_case(name, n_steps=4, extended=False):
     import seqModel as ref_seq            # /root/reference/lstm/seqModel.py
     import embed_attribute as ref_emb     # /root/reference/attributes/embed_attribute.py
-    loss, use_concat, sep, adagrad, lr, clip = LSTM_CASES[name]
+    extra = {}
+    if extended:
+        loss, use_concat, sep, adagrad, lr, clip, extra = LSTMX_CASES[name]
+    else:
+        loss, use_concat, sep, adagrad, lr, clip = LSTM_CASES[name]
     n_users, n_items, dim, mb, T, keep, topk = 40, 30, 8, 12, 5, 0.5, 5
     buckets = [3, T]
     ua, ia, _, l2i = small_dataset(n_users, n_items, 2, 15, 3, 5, 0, None, dim)
@@ -263,6 +276,8 @@ def run_lstm_case(name, n_steps=4):
     rng = np.random.default_rng(5)
     Fu = ua.num_features_cat + ua.num_features_mulhot
     Fi = ia.num_features_cat + ia.num_features_mulhot
+    if extra.get('no_input_item_feature'):
+        Fi = 1                                          # only the id embedding feeds the LSTM (embed_attribute.py:368-369)
     if use_concat:
         params['w_input_user'] = rng.uniform(-.4, .4, (Fu * dim, dim)).astype(np.float32)
         params['w_input_item'] = rng.uniform(-.4, .4, (Fi * dim, dim)).astype(np.float32)
@@ -279,7 +294,7 @@ def run_lstm_case(name, n_steps=4):
     emb = ref_emb.EmbeddingAttribute(rua, ria, mb, None, buckets[-1], sep, i2l_d, l2i_d, devices=devices)
     model = ref_seq.SeqModel(buckets, dim, 1, clip, mb, lr, 0.83, emb, withAdagrad=adagrad, dropoutRate=keep,
                              START_ID=START, loss=loss, devices=devices, use_concat=use_concat, no_user_id=False,
-                             topk_n=topk)
+                             topk_n=topk, **extra)
     g = tf.get_default_graph()
     tfname = {'lstm_w': 'rnn/multi_rnn_cell/cell_0/lstm_cell/weights',
               'lstm_b': 'rnn/multi_rnn_cell/cell_0/lstm_cell/biases'}
@@ -288,6 +303,8 @@ def run_lstm_case(name, n_steps=4):
     back = {v: k for k, v in tfname.items()}
     trainable = sorted(back.get(v._name, v._name) for v in tf.trainable_variables())
     assert trainable == sorted(params.keys()), (trainable, sorted(params.keys()))
+    out_extra = {'output_feat': int(extra.get('output_feat', 1)),
+                 'no_input_item_feature': bool(extra.get('no_input_item_feature', False))}
     masks = MaskQueue(7)
     tf.set_dropout_hook(masks)
     sess = tf.Session()
@@ -296,6 +313,7 @@ def run_lstm_case(name, n_steps=4):
            'n_users': n_users, 'n_items': n_items, 'mb': mb, 'T': T, 'buckets': np.asarray(buckets), 'lr': lr,
            'keep_prob': keep, 'topk': topk, 'n_steps': n_steps, 'START': START, 'clip': clip,
            'l2i': np.asarray(l2i, dtype=np.int64)}
+    out.update(out_extra)
     pack_attributes('u_', ua, out)
     pack_attributes('i_', ia, out)
     for k, v in params.items():
@@ -361,7 +379,7 @@ def run_lstm_case(name, n_steps=4):
     sess.run(model.dropoutAssign_op)
     out['global_step'] = int(model.global_step.numpy())
     tf.set_dropout_hook(None)
-    path = os.path.join(OUT, 'ref_lstm_%s.npz' % name)
+    path = os.path.join(OUT, 'ref_%s_%s.npz' % ('lstmx' if extended else 'lstm', name))
     np.savez_compressed(path, **out)
     print('lstm %-14s losses %s gnorm %s eval %.5f -> %s' % (name, np.round(losses, 4).tolist(),
                                                           np.round(norms, 3).tolist(), ev, os.path.basename(path)))
@@ -445,10 +463,13 @@ def run_cbow_case(name, n_steps=4):
 def main():
     assert os.path.isdir(REF), 'reference sources not found at %s' % REF
     names = sys.argv[1:] or (list(HMF_CASES) + ['hmfeval:warp_eval'] + ['lstm:' + n for n in LSTM_CASES] +
+                             ['lstmx:' + n for n in LSTMX_CASES] +
                              ['cbow:' + n for n in CBOW_CASES])
     for n in names:
         if n == 'hmfeval:warp_eval':
             run_hmf_warp_eval()
+        elif n.startswith('lstmx:'):
+            run_lstm_case(n[6:], extended=True)
         elif n.startswith('lstm:'):
             run_lstm_case(n[5:])
         elif n.startswith('cbow:'):

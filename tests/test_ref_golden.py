@@ -145,9 +145,11 @@ LSTM_CASES = sorted(os.path.basename(p)[len('ref_lstm_'):-4] for p in glob.glob(
 
 
 class SeqCase(object):
-    def __init__(self, name):
-        d = np.load(os.path.join(GOLD, 'ref_lstm_%s.npz' % name))
+    def __init__(self, name, kind='lstm'):
+        d = np.load(os.path.join(GOLD, 'ref_%s_%s.npz' % (kind, name)))
         self.d = d
+        self.output_feat = int(d['output_feat']) if 'output_feat' in d.files else 1
+        self.no_input_item_feature = bool(d['no_input_item_feature']) if 'no_input_item_feature' in d.files else False
         self.loss = str(d['loss'])
         self.use_concat, self.sep, self.adagrad = bool(d['use_concat']), bool(d['sep']), bool(d['adagrad'])
         self.dim, self.mb, self.T = int(d['dim']), int(d['mb']), int(d['T'])
@@ -377,3 +379,75 @@ def test_oracle_reproduces_reference_warp_eval_ranks():
     margin, rank = O.compute_loss(logits, targets, 'warp_eval', mask)
     np.testing.assert_allclose(margin, d['margin_rank'], rtol=2e-5, atol=1e-5)
     assert np.array_equal(np.asarray(rank), d['true_rank'])
+
+
+# ------------------------------------------------------------------ LSTM, non-default flags -----------
+LSTMX_CASES = sorted(os.path.basename(p)[len('ref_lstmx_'):-4] for p in glob.glob(os.path.join(GOLD, 'ref_lstmx_*.npz')))
+
+
+def SeqCaseX(name):
+    return SeqCase(name, 'lstmx')
+
+
+@pytest.mark.parametrize('name', LSTMX_CASES)
+def test_oracle_reproduces_reference_lstm_run_nondefault_flags(name):
+    """output_feat = 0 (score with the id table only) and no_input_item_feature (only the id embedding feeds the
+    LSTM): SURVEY 8(f) row 4, pinned on the CPU oracle."""
+    import torch
+    from oracle.torch_cpu_ref import TorchRefSeq
+    c = SeqCaseX(name)
+    ref = TorchRefSeq(c.ua, c.ia, {k: v.copy() for k, v in c.params.items()}, c.l2i_d, c.i2l_d, loss=c.loss,
+                      keep_prob=c.keep, learning_rate=c.lr, n_sampled=None, dtype=torch.float64, size=c.dim,
+                      use_concat=c.use_concat, no_user_id=False, max_gradient_norm=c.clip, item_output=c.sep,
+                      withAdagrad=c.adagrad, output_feat=c.output_feat, no_input_item_feature=c.no_input_item_feature)
+    for it in range(c.n_steps):
+        users, inp, tgt, w, pos = c.batch('step%d' % it)
+        ref.pos, ref.pos_eval = pos, pos
+        l = ref.step_seq(users, inp, tgt, w, masks=(c.d['step%d/in_masks' % it], c.d['step%d/out_masks' % it]))
+        want = float(c.d['losses'][it])
+        assert abs(l - want) <= 2e-5 * max(1.0, abs(want)), (name, it, l, want)
+        gn = float(c.d['gnorms'][it])
+        assert abs(ref.last_gnorm - gn) <= 1e-4 * max(1.0, gn), (name, it, ref.last_gnorm, gn)
+    for k, v in c.final.items():
+        np.testing.assert_allclose(ref.p[k].detach().numpy().reshape(v.shape), v, rtol=2e-4, atol=2e-5, err_msg=k)
+    users, inp, tgt, w, pos = c.batch('eval')
+    ref.pos, ref.pos_eval = pos, pos
+    ev = ref.step_seq(users, inp, tgt, w, forward_only=True)
+    want = float(c.d['eval/loss'])
+    assert abs(ev - want) <= 2e-5 * max(1.0, abs(want)), (ev, want)
+    assert np.array_equal(ref.topk_seq(users, inp, c.topk), c.d['eval/topk_indexes'])
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: not yet run on a B200; with '
+                   'output_feat = 0 the clip norm of the item multi-hot tables is still taken per table SET '
+                   '(merged) on the CUDA path, per TABLE in the reference (DESIGN.md section 4)')
+@pytest.mark.parametrize('name', LSTMX_CASES)
+def test_cuda_path_reproduces_reference_lstm_run_nondefault_flags(cuda, name):
+    import torch
+    from arecsys_b200 import _lib
+    from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
+    from arecsys_b200.lstm.seqModel import SeqModel
+    c = SeqCaseX(name)
+    _lib.exact_fp32 = True
+    try:
+        params = {k: v.copy() for k, v in c.params.items()}
+        emb = EmbeddingAttribute(c.ua, c.ia, c.mb, None, c.T, c.sep, c.i2l_d, c.l2i_d, params=params)
+        model = SeqModel(c.buckets, c.dim, 1, c.clip, c.mb, c.lr, 0.83, emb, withAdagrad=c.adagrad,
+                         dropoutRate=c.keep, START_ID=c.START, loss=c.loss, use_concat=c.use_concat,
+                         no_user_id=False, topk_n=c.topk, params=params, output_feat=c.output_feat,
+                         no_input_item_feature=c.no_input_item_feature)
+        for it in range(c.n_steps):
+            users, inp, tgt, w, pos = c.batch('step%d' % it)
+            emb.prepare_warp(pos, pos)
+            im = torch.tensor(c.d['step%d/in_masks' % it], device='cuda')
+            om = torch.tensor(c.d['step%d/out_masks' % it], device='cuda')
+            l = model.step(None, users, inp, tgt, w, int(c.d['step%d/bucket' % it]), masks=(im, om))
+            want = float(c.d['losses'][it])
+            assert abs(l - want) <= 2e-4 * max(1.0, abs(want)), (name, it, l, want)
+        dense = model.dense_params()
+        for k, v in c.final.items():
+            got = (emb.params[k] if k in emb.params else dense[k][0]).cpu().numpy()
+            assert np.abs(got.reshape(v.shape) - v).max() <= 2e-3 * max(1.0, np.abs(v).max()), k
+    finally:
+        _lib.exact_fp32 = False

@@ -123,15 +123,11 @@ class EmbeddingAttribute(object):
         _lib.load()
         # shard = (G, r): this GPU stores rows t with t % G == r of every table
         self.shard = shard if (shard is not None and shard[0] > 1) else None
-        # Plan-kernel flavour (library-wide knob): block-aggregated by default; warp-per-bag for the row-sharded
-        # (multi-GPU) step, which was validated with those at N = 2 / 4 and gets the aggregated ones once they have
-        # been measured there, and for tables of >= 2^27 rows (the aggregated kernels key their hash on
-        # (attribute << 27) | row).  ARX_TUNE=plan_agg=.. still wins for A/B runs.
-        vmax = max(list(user_attributes._embedding_classes_list_cat) + list(user_attributes._embedding_classes_list_mulhot) +
-                   list(item_attributes._embedding_classes_list_cat) + list(item_attributes._embedding_classes_list_mulhot) + [0])
+        # Plan-kernel flavour, per model instance (set on the library right before each plan build): block-aggregated
+        # count / fill by default; ARX_TUNE=plan_agg=0 selects the warp-per-bag kernels for A/B runs.  Both key their
+        # (attribute, row) pairs in 32 bits: _TableSet asserts vocab < 2^26.
         tune = dict(kv.split('=') for kv in os.environ.get('ARX_TUNE', '').split(',') if '=' in kv)
-        agg = 0 if (self.shard is not None or vmax >= (1 << 27)) else int(tune.get('plan_agg', 3))
-        _lib.load().arx_set_tuning(b'plan_agg', agg)
+        self.plan_agg = int(tune.get('plan_agg', 3))
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.user_attributes = user_attributes
         self.item_attributes = item_attributes
@@ -671,6 +667,7 @@ class EmbeddingAttribute(object):
         cap_rows = max(min(cap_occ, ts.total_vocab), 1)
         plan = _Plan(self.device, cap_rows, cap_occ, self.dim) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
         _lib.tag = ts.prefix
+        _lib.load().arx_set_tuning(b'plan_agg', self.plan_agg)     # host-side launch-shape choice of THIS model
         call('arx_bwd_plan_begin', plan.c)
         for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
@@ -793,6 +790,23 @@ class EmbeddingAttribute(object):
             ts.pending = []
         for side in forks:
             main.wait_stream(side)
+        # A plan that ran out of capacity makes plan_fill / apply return without touching anything: surface it instead
+        # of training on silently.  Reading the flag synchronises, so: every 256th eager call, never during capture.
+        self._apply_calls = getattr(self, '_apply_calls', 0) + 1
+        if self._apply_calls % 256 == 1 and not torch.cuda.is_current_stream_capturing():
+            self.check_plans()
+
+    def check_plans(self):
+        """Raise ARX_E_CAPACITY if any backward plan of this model overflowed its buffers (counters[2])."""
+        for ts in self.sets.values():
+            plans = list(ts.plans.values()) + ([ts._scratch] if getattr(ts, '_scratch', None) is not None else [])
+            for p in plans:
+                if int(p.counters[2].item()) != 0:
+                    for n in ts.names:
+                        self.touch[n].zero_()              # plan_reset only cleared the rows it had recorded
+                    p.counters.zero_()
+                    raise RuntimeError('backward plan of table set %r exceeded its capacity (ARX_E_CAPACITY): '
+                                       'cap_rows=%d cap_occ=%d' % (ts.prefix, p.cap_rows, p.cap_occ))
 
     def side_stream(self, k):
         """Streams 8.. carry the backward-plan builds: thousands of small latency-bound CTAs that would

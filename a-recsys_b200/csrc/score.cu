@@ -214,6 +214,11 @@ loss_rows_kernel(const float* __restrict__ scores, long long V, long long ld,
     const unsigned int h = (unsigned int)v & (kFilterBits - 1);
     if (!((filt[h >> 5] >> (h & 31)) & 1u)) return false;
     if (exact) return true;
+    if (kind == ARX_LOSS_MW) {                  // pool-position columns are in item order (unsorted, -1 = not in
+      for (int i = p0; i < p1; ++i)             // the pool): confirm a (rare) filter hit with a linear scan
+        if (pos_idx[i] == (int)v) return true;
+      return false;
+    }
     int lo = p0, hi = p1;                       // binary search in the sorted slice
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;

@@ -45,6 +45,7 @@ class _Saver(object):
         m = self.model
         if global_step is not None:
             path = '%s-%d' % (path, global_step)
+        path = self._shard_path(path)
         state = {'params': {k: v.cpu() for k, v in m.att_emb.params.items()},
                  'accs': {k: v.cpu() for k, v in m.att_emb.accs.items()},
                  'dense': {k: v.detach().cpu() for k, v in m.dense.items()},
@@ -55,9 +56,16 @@ class _Saver(object):
             f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
         return path
 
+    def _shard_path(self, path):
+        """Row-sharded tables: every rank owns different rows, so each writes / reads its own file."""
+        sh = self.model.att_emb.shard
+        if sh is not None and '.shard' not in os.path.basename(path):
+            path = '%s.shard%dof%d' % (path, sh[1], sh[0])
+        return path
+
     def restore(self, sess, path):
         m = self.model
-        state = torch.load(path, map_location='cpu')
+        state = torch.load(self._shard_path(path), map_location='cpu')
         for k, v in state['params'].items():
             m.att_emb.params[k].copy_(v)
         for k, v in state['accs'].items():
@@ -369,6 +377,7 @@ class LatentProductModel(object):
         self._g_users = users_dev.to(torch.int32).clone()
         self._g_items = items_dev.to(torch.int32).clone()
         self._g_loss_kind = loss
+        self._g_lr = self.learning_rate.eval()
         single = self.att_emb.shard is None
         # high priority on one GPU (see EmbeddingAttribute.side_stream); default streams for the sharded step
         side = torch.cuda.Stream(priority=-1) if single else torch.cuda.Stream()
@@ -386,13 +395,43 @@ class LatentProductModel(object):
         self.global_step.assign(gs)
 
     def replay_step(self, users, items, sync=True):
-        """One captured training step on new ids (device or pinned-host int32 tensors)."""
+        """One captured training step on new ids (device or pinned-host int32 tensors).
+        sync=True   : returns this step's loss as a float (H2D -> graph -> D2H, serialised);
+        sync='lag'  : the training-loop form: this step's loss is copied to pinned host memory behind the graph and
+                      the PREVIOUS step's loss is returned (None on the first call), so the host never waits for the
+                      step it has just launched; flush_loss() returns the last one;
+        sync=False  : returns the device scalar."""
+        if self.learning_rate.eval() != self._g_lr:
+            # the learning rate is a kernel argument baked into the captured launches
+            raise RuntimeError('learning rate changed after capture_step(): capture again (learning_rate_decay_op)')
         self._g_users.copy_(users, non_blocking=True)
         self._g_items.copy_(items, non_blocking=True)
         self._graph.replay()
         _lib.launch_count += self._g_launches
         self.global_step.assign(self.global_step.eval() + 1)
-        return float(self._g_loss.item()) if sync else self._g_loss
+        if sync == 'lag':
+            prev = self.flush_loss()
+            if not hasattr(self, '_g_host'):
+                self._g_host = [torch.empty(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+                self._g_slot = 0
+            self._g_slot ^= 1
+            self._g_host[self._g_slot].copy_(self._loss_for_host().reshape(1), non_blocking=True)
+            self._g_ev = torch.cuda.Event()
+            self._g_ev.record()
+            return prev
+        return float(self._loss_for_host().item()) if sync else self._g_loss
+
+    def _loss_for_host(self):
+        return self._g_loss
+
+    def flush_loss(self):
+        """Loss of the last replay_step(sync='lag') call (waits for that step), or None."""
+        ev = getattr(self, '_g_ev', None)
+        if ev is None:
+            return None
+        ev.synchronize()
+        self._g_ev = None
+        return float(self._g_host[self._g_slot][0])
 
     # ------------------------------------------------------------------ batching ------
     def get_batch(self, data, loss='ce', hist=None):

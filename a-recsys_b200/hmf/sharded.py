@@ -102,9 +102,12 @@ class ShardedLatentProductModel(LatentProductModel):
 
     def replay_step(self, users, items, sync=True):
         """Captured sharded step (the NCCL exchanges are part of the graph); users / items are the
-        GLOBAL batch.  With sync the global mean loss is all-reduced and returned as a float."""
-        loss = super(ShardedLatentProductModel, self).replay_step(users, items, sync=False)
-        if not sync:
-            return loss
-        tot = self.ex.all_reduce(loss.clone())
-        return float(tot.item())
+        GLOBAL batch.  With sync the global mean loss is all-reduced and returned as a float; sync='lag' returns
+        the previous step's (see LatentProductModel.replay_step): no host wait on the step just launched."""
+        if sync is False:
+            return super(ShardedLatentProductModel, self).replay_step(users, items, sync=False)
+        return super(ShardedLatentProductModel, self).replay_step(users, items, sync=sync)
+
+    def _loss_for_host(self):
+        # the rank-local partial of the global mean -> global mean (one 4-byte all-reduce, stream-ordered)
+        return self.ex.all_reduce(self._g_loss.clone())

@@ -154,10 +154,10 @@ def algorithmic_bytes(att, ids, dim, with_bias):
     return dict(occ=occ, uniq=uniq, fwd_nominal=fwd_nom, fwd_unique=fwd_uni, bwd_nominal=bwd_nom, bwd_unique=bwd_uni)
 
 
-def cpu_baseline(a, ua, ia, l2i, users, items, pos, sampler_pop, sampler_p, steps, warm=1):
+def cpu_baseline(a, ua, ia, l2i, users, items, pos, sampler_pop, sampler_p, steps, warm=1, threads=None):
     """The reference's literal op sequence on the host cores (oracle/torch_cpu_ref.py), bounded sample."""
     from oracle.torch_cpu_ref import TorchRefHMF
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     rng = np.random.default_rng(1)
     dim = a.dim
     lim = 0.05
@@ -212,14 +212,18 @@ def main():
         if rank != 0:
             return
         ua, ia, i2l, l2i, users, items, pop, p, pos = build_workload(a, 0, 1)
-        v, ms = cpu_baseline(a, ua, ia, l2i, users, items, pos, pop, p, max(1, min(a.steps, a.cpu_steps)),
-                             warm=1 if a.warmup else 0)
-        sample = '%d-row batches (of the %d-row step), %d timed steps, literal token-score order' % (
-            a.cpu_mb, a.mb, max(1, min(a.steps, a.cpu_steps)))
+        # each timed step = one bounded SAMPLE of the C2 step: a.cpu_mb rows of the 4096-row batch through the
+        # reference's literal op order (at 4096 rows that order materialises a [10^6, 4096] fp32 token-score
+        # matrix per id table = 16 GB; the sample keeps the arm within minutes).  Exactly --steps timed steps
+        # after --warmup untimed ones; throughput = rows really processed / time.
+        v, ms = cpu_baseline(a, ua, ia, l2i, users, items, pos, pop, p, max(1, a.steps), warm=max(0, a.warmup))
+        sample = ('each step = %d rows of the %d-row C2 batch, literal token-score order; %d timed steps after %d '
+                  'warm-up steps; all %d host threads' % (a.cpu_mb, a.mb, max(1, a.steps), max(0, a.warmup),
+                                                          os.cpu_count() or 1))
         print(json.dumps({'impl': 'reference', 'metric': 'interactions/sec', 'value': v, 'unit': 'interactions/s',
                           'n_gpus': a.gpus, 'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms,
-                          'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                          'data': 'synthetic', 'config': cfg,
+                          'rows_per_step': a.cpu_mb, 'higher_is_better': True, 'scaling': 'weak',
+                          'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg, 'sample': sample,
                           'cpu_baseline': {'value': v, 'unit': 'interactions/s', 'cores': os.cpu_count(),
                                            'kind': 'port', 'sample': sample},
                           'e2e': {'value': v, 'unit': 'interactions/s', 'h2d_bytes_per_step': 0,
@@ -266,9 +270,13 @@ def main():
     state = {'step': 0, 'graph': False}
     use_graph = not a.no_graph           # N > 1: the NCCL exchanges are captured with the kernels
 
+    # pool refresh every n_resample steps, phased so that a refresh falls INSIDE the timed window even when the
+    # driver times only 20 steps (then 1 refresh per 20 steps: above the real 1-in-50 rate, i.e. conservative)
+    refresh_at = (a.warmup + 2 + min(10, a.steps // 2)) % a.n_resample
+
     def run_step(u, it, sync):
         sampled = None
-        if a.loss == 'mw' and state['step'] % a.n_resample == 0:
+        if a.loss == 'mw' and (state['step'] == 0 or state['step'] % a.n_resample == refresh_at):
             sampled = sampler.sample(a.n_sampled)
             if world > 1:
                 torch.distributed.broadcast(sampled, 0)       # every rank must score the same pool
@@ -279,6 +287,27 @@ def main():
             return model.replay_step(u, it, sync=sync)
         return model.step(None, u, it, None, sampled, None, loss=a.loss, sync=sync)
 
+    # ---------------- N > 1: the sharded step must compute what the single-GPU step computes ----------
+    sharded_check = None
+    if world > 1:
+        ones = torch.ones((a.mb, a.dim), dtype=torch.float32, device=dev)           # dropout mask injected: all kept
+        pool0 = sampler.sample(a.n_sampled)
+        torch.distributed.broadcast(pool0, 0)
+        l_sh = model.step(None, u_dev[0], i_dev[0], None, pool0, None, loss=a.loss, masks=[ones], sync=True)
+        if rank == 0:
+            single = LatentProductModel(a.n_users, a.n_items, a.dim, 1, mb, a.lr, 1.0, ua, ia, i2l, l2i,
+                                        loss_function=a.loss, dropout=a.keep_prob, n_sampled=n_sampled, seed=1)
+            single.prepare_warp(pos, pos)
+            l_1 = single.step(None, u_dev[0], i_dev[0], None, pool0, None, loss=a.loss,
+                              masks=[torch.ones((mb, a.dim), dtype=torch.float32, device=dev)], sync=True)
+            ok = abs(l_sh - l_1) <= 1e-3 * max(1.0, abs(l_1))
+            sharded_check = {'loss_sharded': l_sh, 'loss_single_gpu': l_1, 'ok': bool(ok),
+                             'what': 'step 0, same global batch / pool / weights, dropout mask of ones'}
+            del single
+            torch.cuda.empty_cache()
+            assert ok, 'sharded step disagrees with the single-GPU step: %r' % (sharded_check,)
+        state['step'] += 1
+        barrier()
     # ---------------- value: ids resident in HBM ---------------------------------------
     for s in range(a.warmup):
         run_step(u_dev[s], i_dev[s], False)
@@ -299,19 +328,46 @@ def main():
     launches = _lib.launch_count - l0
     ms_total = ev0.elapsed_time(ev1)
     # ---------------- e2e: host ids -> H2D -> step -> loss D2H -------------------------
+    # The training-loop form of the public API: every step copies its ids from pinned host memory, replays the
+    # step and copies its loss back to the host; the host reads the loss one step late (replay_step(sync='lag')),
+    # so it never stalls on the step it has just launched.  The last loss is read before the clock stops.
+    def e2e_step(s):
+        u = u_host[nb + s].to(dev, non_blocking=True)
+        it = i_host[nb + s].to(dev, non_blocking=True)
+        if state['graph']:
+            return run_step(u, it, 'lag')
+        return run_step(u, it, True)
     for s in range(min(a.warmup, 5)):
-        run_step(u_host[nb + s].to(dev, non_blocking=True), i_host[nb + s].to(dev, non_blocking=True), True)
+        e2e_step(s)
+    if state['graph']:
+        model.flush_loss()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     last = 0.0
     for s in range(a.warmup, nb):
-        last = run_step(u_host[nb + s].to(dev, non_blocking=True), i_host[nb + s].to(dev, non_blocking=True), True)
+        l = e2e_step(s)
+        last = l if l is not None else last
+    if state['graph']:
+        last = model.flush_loss()
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     wall_e2e = (time.perf_counter() - t0) * 1e3
+    # the reference-facing call as a reference user makes it (B3): model.step(session, [python ints], [python ints])
+    # -> python float, eager launches, synchronous loss; a bounded number of steps
+    n_list = min(a.steps, 20)
+    lists = [(u_host[nb + s].tolist(), i_host[nb + s].tolist()) for s in range(n_list)]
+    g_was, state['graph'] = state['graph'], False
+    run_step(lists[0][0], lists[0][1], True)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(n_list):
+        run_step(lists[s][0], lists[s][1], True)
+    barrier()
+    wall_lists = (time.perf_counter() - t0) * 1e3
+    state['graph'] = g_was
     clk = clocks.stop()
     # ---------------- per-kernel CUDA-event durations (separate pass: the event pairs would
     # otherwise perturb `value`); same batches, same stream -------------------------------
@@ -322,9 +378,9 @@ def main():
     tl, _lib.timeline = _lib.timeline, None
 
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, wall_e2e, wall_lists], device=dev, dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        ms_total, ms_e2e = float(t[0]), float(t[1])
+        ms_total, ms_e2e, wall_e2e, wall_lists = (float(x) for x in t)
     if rank != 0:
         return
     ms_step = ms_total / a.steps
@@ -355,9 +411,23 @@ def main():
                       'frac': nbytes_unique / us / 1e3 / peak, 'traffic': None,
                       'achieved_nominal': nbytes_nominal / us / 1e3, 'algorithmic_bytes': nbytes_unique,
                       'algorithmic_bytes_nominal': nbytes_nominal, 'avg_us': us, 'kernel': what, 'peak_source': peak_src}
+    step_roof = None
     if world == 1:       # per-rank byte counts under sharding are 1/N of these: roofline only at N=1
         roof('arx_pool_fwd:user', ub['fwd_unique'], ub['fwd_nominal'], 'pool_fwd_flat_kernel<1> user side, %d bags' % (a.mb * (a.n_mulhot + 1)))
         roof('arx_pool_bwd_apply:user', ub['bwd_unique'], ub['bwd_nominal'], 'pool_bwd_apply_kernel<4> user side')
+        # item side: the sampled pool and the target items are two lookups whose gradients are de-duplicated
+        # together (one plan, one apply launch); byte counts use the pool that is current at the end of the run
+        if a.loss == 'mw' and model.att_emb.sampled_ids is not None:
+            pool_ids = model.att_emb.sampled_ids.cpu().numpy().astype(np.int64)
+            ib2 = algorithmic_bytes(ia, np.concatenate([pool_ids, item_ids.astype(np.int64)]), a.dim, True)
+            roof('arx_pool_bwd_apply:item', ib2['bwd_unique'], ib2['bwd_nominal'],
+                 'pool_bwd_apply_kernel<4> item side (pool + targets, %d entity rows)' % (len(pool_ids) + len(item_ids)))
+            # whole step against the HBM roofline: embedding forward + backward bytes of both sides,
+            # unique-row accounting, over the measured step time (everything else in the step counts as overhead)
+            step_bytes = ub['fwd_unique'] + ub['bwd_unique'] + ib2['fwd_unique'] + ib2['bwd_unique']
+            step_roof = {'bound': 'hbm', 'algorithmic_bytes': step_bytes, 'achieved': step_bytes / (ms_step * 1e-3) / 1e9,
+                         'peak': peak, 'unit': 'GB/s', 'frac': step_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                         'what': 'embedding fwd+bwd bytes of both sides (unique rows) / ms_per_step', 'peak_source': peak_src}
     dom = max(roofs, key=lambda k: per_kernel[k]['ms_per_step']) if roofs else None
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
     # dram bytes per launch from the committed ncu --set full capture (profiles/r1_ncu_summary.md; the first
@@ -376,7 +446,14 @@ def main():
            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
            'clocks': clk,
            'e2e': {'value': e2e_v, 'unit': 'interactions/s', 'h2d_bytes_per_step': 2 * mb * 4,
-                   'd2h_bytes_per_step': 4, 'ms_per_step': max(ms_e2e, wall_e2e) / a.steps, 'last_loss': last},
+                   'd2h_bytes_per_step': 4, 'ms_per_step': max(ms_e2e, wall_e2e) / a.steps, 'last_loss': last,
+                   'api': "model.replay_step(pinned host ids, sync='lag'): per step H2D of the ids, the captured "
+                          "step, D2H of the loss (read by the host one step late; the last one before the clock stops)",
+                   'via_model_step_lists': {'value': mb * n_list / (wall_lists / 1e3), 'unit': 'interactions/s',
+                                            'ms_per_step': wall_lists / n_list, 'steps': n_list,
+                                            'api': 'model.step(None, [python ints], [python ints]) -> float, as the '
+                                                   'reference runner calls it (eager launches, synchronous loss)'}},
+           'roofline_step': step_roof, 'sharded_check': sharded_check,
            'gpu_launches': launches, 'launch_mode': 'cuda graph replay (1 graph launch per step)' if use_graph else 'eager',
            'roofline': roofs.get(dom), 'roofline_all': roofs, 'per_kernel': per_kernel,
            'batch_stats': {'user_occurrences': ub['occ'], 'user_unique_rows': ub['uniq'],
@@ -385,6 +462,10 @@ def main():
         del model
         torch.cuda.empty_cache()
         v, ms = cpu_baseline(a, ua, ia, l2i, users, items, pos, pop, p, a.cpu_steps)
+        v1, ms1 = cpu_baseline(a, ua, ia, l2i, users, items, pos, pop, p, 1, warm=1, threads=1)
+        out['cpu_baseline_1thread'] = {'value': v1, 'unit': 'interactions/s', 'cores': 1, 'kind': 'port',
+                                       'ms_per_step': ms1, 'sample': '%d-row batch, 1 timed step after 1 warm-up, '
+                                       'torch.set_num_threads(1)' % a.cpu_mb}
         out['cpu_baseline'] = {'value': v, 'unit': 'interactions/s', 'cores': os.cpu_count(), 'kind': 'port',
                                'ms_per_step': ms,
                                'sample': '%d-row batches (of the %d-row step), %d timed steps after 1 warm-up, '

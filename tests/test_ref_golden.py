@@ -419,9 +419,6 @@ def test_oracle_reproduces_reference_lstm_run_nondefault_flags(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason='added after the round-1 GPU budget was spent: not yet run on a B200; with '
-                   'output_feat = 0 the clip norm of the item multi-hot tables is still taken per table SET '
-                   '(merged) on the CUDA path, per TABLE in the reference (DESIGN.md section 4)')
 @pytest.mark.parametrize('name', LSTMX_CASES)
 def test_cuda_path_reproduces_reference_lstm_run_nondefault_flags(cuda, name):
     import torch

@@ -67,6 +67,8 @@ SIGNATURES = {
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_lstm_gates_fwd2': [vp, vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd2': [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    'arx_lstm_seq_fwd': [vp, vp, vp, vp, i64, i64, i32, f32, vp],
+    'arx_lstm_seq_bwd': [vp, vp, vp, vp, i64, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
     'arx_sum_over_steps': [vp, i64, i64, i32, f32, vp, vp],
     'arx_transpose': [vp, i64, i64, vp, i32, vp],
@@ -145,7 +147,8 @@ def call(name, *args):
     return rc
 
 
-_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd')
+_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd', 'arx_lstm_seq_fwd',
+                       'arx_lstm_seq_bwd')
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 

@@ -516,8 +516,13 @@ class EmbeddingAttribute(object):
             pos_row = pos_rows if pos_rows is not None else self.u_indices['input']
         rank = torch.empty((mb,), dtype=torch.int64, device=self.device) if (true_rank or loss == 'warp_eval') else None
         dts = torch.empty((mb,), dtype=torch.float32, device=self.device) if (loss == 'mw' and want_grad) else None
+        kind, func = _lib.LOSS_KIND[loss], _lib.LOSS_FUNC[loss_func]
+        if loss == 'warp_eval':
+            # _compute_warp_eval_loss (:620-639) reports the RAW margin rank sum_v mask * relu(1 + s_v - s_t), not its
+            # log: the hinge sum with the identity transform (found by the golden test through model.step)
+            kind, func = _lib.LOSS_KIND['rs'], _lib.LOSS_FUNC['linear']
         call('arx_loss_rows', logits.data_ptr(), mb, V, logits.stride(0), ptr(tgt), ptr(ts), ptr(pos_row),
-             ptr(pos_ptr), ptr(pos_idx), _lib.LOSS_KIND[loss], _lib.LOSS_FUNC[loss_func], float(exp_p),
+             ptr(pos_ptr), ptr(pos_idx), kind, func, float(exp_p),
              ptr(row_scale), out.data_ptr(), logits.data_ptr() if want_grad else None, ptr(dts), ptr(rank))
         self._last_dtarget = dts
         if loss == 'warp_eval' or true_rank:

@@ -21,7 +21,7 @@ from .. import _lib
 from .._lib import POOL_MEAN, POOL_CONCAT, OPT_ADAGRAD, OPT_SGD, call, ptr
 from ..attributes import embed_attribute
 from ..hmf.hmf_model import _Var
-from .lstm_layer import LSTMLayer
+from .lstm_layer import LSTMLayer, LSTMStack
 
 
 class _Saver(object):
@@ -80,8 +80,7 @@ class SeqModel(object):
         self.size = size
         self.max_gradient_norm = max_gradient_norm
         self.withAdagrad = withAdagrad
-        if num_layers != 1:
-            raise NotImplementedError('num_layers > 1 (MultiRNNCell) is not implemented on the CUDA path yet')
+        self.num_layers = max(1, int(num_layers))
         if loss not in ('ce', 'warp', 'mw'):
             print('Error: not implemented other loss!!')
             exit(1)
@@ -115,7 +114,7 @@ class SeqModel(object):
             d_in = size
         else:
             d_in = m.dim
-        self.cell = LSTMLayer(d_in, size, self.device, gen, p.get('lstm_w'), p.get('lstm_b'))
+        self.cell = LSTMStack(d_in, size, self.num_layers, self.device, gen, p)       # MultiRNNCell (seqModel.py:99-103)
         self.dense_acc = {k: torch.full_like(v[0], embed_attribute.ADAGRAD_INIT_ACC)
                           for k, v in self.dense_params().items()}
         if self.loss in ["warp", "mw"]:
@@ -207,8 +206,9 @@ class SeqModel(object):
         train = not forward_only
 
         X, ictx = self._inputs(users, item_ids, T, mb)
-        in_mask, out_mask = masks if masks is not None else (None, None)
-        Hout = self.cell.forward(X, keep, in_mask, out_mask)                  # [T, mb, H]
+        # masks = (input masks of layer 0, output masks of the stack[, input masks of layer 1, ...])
+        in_mask, out_mask = (masks[0], masks[1]) if masks is not None else (None, None)
+        Hout = self.cell.forward(X, keep, in_mask, out_mask, tuple(masks[2:]) if masks is not None else ())   # [T, mb, H]
         Hf = Hout.reshape(T * mb, self.size)
 
         eff = self.loss

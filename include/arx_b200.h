@@ -27,7 +27,7 @@ extern "C" {
 #define ARX_E_UNSUPPORTED  -3
 #define ARX_E_CAPACITY     -4
 
-#define ARX_ABI_VERSION     2
+#define ARX_ABI_VERSION     3
 #define ARX_MAX_ATTRS      64
 
 /* One attribute (= one embedding table) of one entity side.  Mirrors the per-attribute
@@ -278,6 +278,20 @@ int arx_lstm_gates_fwd2(float* Z, const float* c_prev, float* c, float* h, float
 int arx_lstm_gates_bwd2(float* G, const float* c_prev, const float* c, const float* dh_out,
                         const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
                         int round_tf32_out, void* stream);
+/* K8 as ONE persistent kernel per direction (lstm/seqModel.py:99-103,477: static_rnn over LSTMCell): a cluster of
+ * H/32 CTAs owns 128 batch rows for all T steps, W_h resident in shared memory, h W_h on tcgen05 / TMEM, gate
+ * non-linearities in the TMEM epilogue, the hidden state all-gathered between the CTAs through distributed shared
+ * memory; the backward kernel reduce-scatters the partial dh tiles the same way.
+ *   fwd: G [T, mb, 4H] = x-projection + bias on entry, ACTIVATED gates (i, j, f, o) on return; WhT [4H, H] = W_h^T
+ *        (tf32-rounded); Hs / Cs [T+1, mb, H]: slots 1..T are written (slot 0 = the caller's zero state); h is stored
+ *        tf32-rounded (it only feeds tensor-core contractions).
+ *   bwd: G = activated gates on entry, dZ (tf32-rounded) on return; Wh [H, 4H] = W_h (tf32-rounded); Cs from the
+ *        forward; dH [T, mb, H] = gradient w.r.t. the step outputs.
+ * ARX_E_UNSUPPORTED unless H is 32, 64 or 128: the caller then runs the per-step kernels above. */
+int arx_lstm_seq_fwd(float* G, const float* WhT, float* Hs, float* Cs, int64_t T, int64_t mb, int H,
+                     float forget_bias, void* stream);
+int arx_lstm_seq_bwd(float* G, const float* Wh, const float* Cs, const float* dH, int64_t T, int64_t mb, int H,
+                     void* stream);
 /* K9 — LSTM / CBOW input mixing: y[r,:] = a*x1[r,:] + b*x2[r % rep,:] (reduce_mean([user_embed,
  * item_embed], 0), lstm/seqModel.py:155; x2 broadcast over the T steps) and the adjoint of the
  * broadcast: out[r,:] = scale * sum_t x[t*rep + r,:]. */

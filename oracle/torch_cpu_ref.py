@@ -228,8 +228,9 @@ class TorchRefSeq(TorchRefHMF):
     params additionally hold 'lstm_w' [d_in+H, 4H], 'lstm_b' [4H] (+ 'w_input_user'/'w_input_item')."""
 
     def __init__(self, *a, size=8, use_concat=False, no_user_id=False, no_input_item_feature=False,
-                 max_gradient_norm=5.0, withAdagrad=True, item_output=False, output_feat=1, **kw):
+                 max_gradient_norm=5.0, withAdagrad=True, item_output=False, output_feat=1, num_layers=1, **kw):
         super(TorchRefSeq, self).__init__(*a, **kw)
+        self.num_layers = num_layers            # MultiRNNCell([DropoutWrapper(LSTMCell, in)] * n) then DropoutWrapper(out): seqModel.py:99-103
         self.output_feat = output_feat          # 0: score with the id table only (embed_attribute.py:164-165)
         self.size, self.use_concat, self.no_user_id = size, use_concat, no_user_id
         self.no_input_item_feature = no_input_item_feature
@@ -301,10 +302,11 @@ class TorchRefSeq(TorchRefHMF):
             uproj = ue @ self.p['w_input_user']
         else:
             ue = self._emb('user', self.ua, users, False, no_id=self.no_user_id)
-        W, b = self.p['lstm_w'], self.p['lstm_b']
+        L = self.num_layers
+        Ws = [(self.p['lstm_w' + ('_%d' % l if l else '')], self.p['lstm_b' + ('_%d' % l if l else '')]) for l in range(L)]
         H = self.size
-        h = torch.zeros((mb, H), dtype=self.dtype)
-        c = torch.zeros((mb, H), dtype=self.dtype)
+        hs = [torch.zeros((mb, H), dtype=self.dtype) for _ in range(L)]
+        cs = [torch.zeros((mb, H), dtype=self.dtype) for _ in range(L)]
         eff = 'warp' if (self.loss == 'mw' and forward_only) else self.loss
         num = torch.zeros(mb, dtype=self.dtype)
         den = torch.zeros(mb, dtype=self.dtype)
@@ -318,12 +320,20 @@ class TorchRefSeq(TorchRefHMF):
             else:
                 ie = self._emb('item', self.ia, item_inputs[t], False, no_attribute=self.no_input_item_feature)
                 x = torch.stack([ue, ie], 0).mean(0)
-            x = self._drop(x, keep, masks[0][t] if masks is not None else None)
-            z = torch.cat([x, h], 1) @ W + b
-            i, j, f, o = torch.split(z, H, dim=1)
-            c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
-            h = torch.sigmoid(o) * torch.tanh(c)
-            out = self._drop(h, keep, masks[1][t] if masks is not None else None)
+            # masks = (in_masks of layer 0, out_masks[, in_masks of layer 1, ...]): every layer has its own input
+            # dropout, the stack one output dropout
+            for l in range(L):
+                mk = None
+                if masks is not None:
+                    mk = masks[0][t] if l == 0 else masks[1 + l][t]
+                x = self._drop(x, keep, mk)
+                W, b = Ws[l]
+                z = torch.cat([x, hs[l]], 1) @ W + b
+                i, j, f, o = torch.split(z, H, dim=1)
+                cs[l] = torch.sigmoid(f + 1.0) * cs[l] + torch.sigmoid(i) * torch.tanh(j)
+                hs[l] = torch.sigmoid(o) * torch.tanh(cs[l])
+                x = hs[l]
+            out = self._drop(x, keep, masks[1][t] if masks is not None else None)
             wt = torch.as_tensor(np.asarray(weights[t]), dtype=self.dtype)
             if eff == 'mw':
                 logits = self._pred(out, 'sampled')
@@ -345,9 +355,10 @@ class TorchRefSeq(TorchRefHMF):
                 uproj = self._emb('user', self.ua, users, True, no_id=self.no_user_id) @ self.p['w_input_user']
             else:
                 ue = self._emb('user', self.ua, users, False, no_id=self.no_user_id)
-            W, b, H = self.p['lstm_w'], self.p['lstm_b'], self.size
-            h = torch.zeros((mb, H), dtype=self.dtype)
-            c = torch.zeros((mb, H), dtype=self.dtype)
+            H, L = self.size, self.num_layers
+            Ws = [(self.p['lstm_w' + ('_%d' % l if l else '')], self.p['lstm_b' + ('_%d' % l if l else '')]) for l in range(L)]
+            hs = [torch.zeros((mb, H), dtype=self.dtype) for _ in range(L)]
+            cs = [torch.zeros((mb, H), dtype=self.dtype) for _ in range(L)]
             out = []
             for t in range(T):
                 if self.use_concat:
@@ -356,11 +367,14 @@ class TorchRefSeq(TorchRefHMF):
                 else:
                     ie = self._emb('item', self.ia, item_inputs[t], False, no_attribute=self.no_input_item_feature)
                     x = torch.stack([ue, ie], 0).mean(0)
-                z = torch.cat([x, h], 1) @ W + b
-                i, j, f, o = torch.split(z, H, dim=1)
-                c = torch.sigmoid(f + 1.0) * c + torch.sigmoid(i) * torch.tanh(j)
-                h = torch.sigmoid(o) * torch.tanh(c)
-                prob = torch.softmax(self._pred(h, 'full'), 1)
+                for l in range(L):
+                    W, b = Ws[l]
+                    z = torch.cat([x, hs[l]], 1) @ W + b
+                    i, j, f, o = torch.split(z, H, dim=1)
+                    cs[l] = torch.sigmoid(f + 1.0) * cs[l] + torch.sigmoid(i) * torch.tanh(j)
+                    hs[l] = torch.sigmoid(o) * torch.tanh(cs[l])
+                    x = hs[l]
+                prob = torch.softmax(self._pred(x, 'full'), 1)
                 out.append(torch.sort(prob, dim=1, descending=True, stable=True)[1][:, :k])
             return torch.stack(out, 0).numpy()
 

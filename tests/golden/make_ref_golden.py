@@ -258,6 +258,8 @@ LSTMX_CASES = {
     # (use_concat + no_input_item_feature is not usable in the reference: w_input_item keeps the full concat width,
     #  seqModel.py:135-137 vs embed_attribute.py:368-369)
     'warp_noitemfeat': ('warp', False, False, True, 0.5, 5.0, {'no_input_item_feature': True}),
+    # MultiRNNCell([DropoutWrapper(LSTMCell, in)] * 2) + DropoutWrapper(out) (seqModel.py:99-103)
+    'ce_2layers': ('ce', False, False, True, 0.5, 5.0, {'num_layers': 2}),
 }
 
 
@@ -267,6 +269,7 @@ def run_lstm_case(name, n_steps=4, extended=False):
     extra = {}
     if extended:
         loss, use_concat, sep, adagrad, lr, clip, extra = LSTMX_CASES[name]
+        extra = dict(extra)
     else:
         loss, use_concat, sep, adagrad, lr, clip = LSTM_CASES[name]
     n_users, n_items, dim, mb, T, keep, topk = 40, 30, 8, 12, 5, 0.5, 5
@@ -283,6 +286,10 @@ def run_lstm_case(name, n_steps=4, extended=False):
         params['w_input_item'] = rng.uniform(-.4, .4, (Fi * dim, dim)).astype(np.float32)
     params['lstm_w'] = rng.uniform(-.4, .4, (2 * dim, 4 * dim)).astype(np.float32)
     params['lstm_b'] = np.zeros(4 * dim, dtype=np.float32)
+    n_layers = int(extra.pop('num_layers', 1))
+    for l in range(1, n_layers):
+        params['lstm_w_%d' % l] = rng.uniform(-.4, .4, (2 * dim, 4 * dim)).astype(np.float32)
+        params['lstm_b_%d' % l] = np.zeros(4 * dim, dtype=np.float32)
     START = n_items
     l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
     i2l_d = {v: k for k, v in l2i_d.items()}
@@ -292,19 +299,23 @@ def run_lstm_case(name, n_steps=4, extended=False):
     devices = ['/cpu:0'] * 3
     rua, ria = to_ref_attributes(ua, dim), to_ref_attributes(ia, dim)
     emb = ref_emb.EmbeddingAttribute(rua, ria, mb, None, buckets[-1], sep, i2l_d, l2i_d, devices=devices)
-    model = ref_seq.SeqModel(buckets, dim, 1, clip, mb, lr, 0.83, emb, withAdagrad=adagrad, dropoutRate=keep,
+    model = ref_seq.SeqModel(buckets, dim, n_layers, clip, mb, lr, 0.83, emb, withAdagrad=adagrad, dropoutRate=keep,
                              START_ID=START, loss=loss, devices=devices, use_concat=use_concat, no_user_id=False,
                              topk_n=topk, **extra)
     g = tf.get_default_graph()
     tfname = {'lstm_w': 'rnn/multi_rnn_cell/cell_0/lstm_cell/weights',
               'lstm_b': 'rnn/multi_rnn_cell/cell_0/lstm_cell/biases'}
+    for l in range(1, n_layers):
+        tfname['lstm_w_%d' % l] = 'rnn/multi_rnn_cell/cell_%d/lstm_cell/weights' % l
+        tfname['lstm_b_%d' % l] = 'rnn/multi_rnn_cell/cell_%d/lstm_cell/biases' % l
     for k, v in params.items():
         g.by_name[tfname.get(k, k)].load(v)
     back = {v: k for k, v in tfname.items()}
     trainable = sorted(back.get(v._name, v._name) for v in tf.trainable_variables())
     assert trainable == sorted(params.keys()), (trainable, sorted(params.keys()))
     out_extra = {'output_feat': int(extra.get('output_feat', 1)),
-                 'no_input_item_feature': bool(extra.get('no_input_item_feature', False))}
+                 'no_input_item_feature': bool(extra.get('no_input_item_feature', False)),
+                 'num_layers': n_layers}
     masks = MaskQueue(7)
     tf.set_dropout_hook(masks)
     sess = tf.Session()
@@ -350,12 +361,15 @@ def run_lstm_case(name, n_steps=4, extended=False):
         fetched = [f for f in sess.fetch_log if isinstance(f, list) and len(f) == 3][-1]   # [loss, update, norm]
         losses.append(float(lval))
         norms.append(float(fetched[2]))
-        order = sorted(masks.by_node, key=lambda kv: kv[0])     # graph order: in_0, out_0, in_1, out_1, ...
-        assert len(order) == 2 * Tb, len(order)
+        order = sorted(masks.by_node, key=lambda kv: kv[0])     # graph order per time step: in (layer 0), [in (layer 1), ...], out
+        per = n_layers + 1
+        assert len(order) == per * Tb, len(order)
         put('step%d' % it, users, inp, tgt, w, pos)
         out['step%d/bucket' % it] = b
-        out['step%d/in_masks' % it] = np.stack([m for _, m in order[0::2]])
-        out['step%d/out_masks' % it] = np.stack([m for _, m in order[1::2]])
+        out['step%d/in_masks' % it] = np.stack([m for _, m in order[0::per]])
+        for l in range(1, n_layers):
+            out['step%d/in_masks_%d' % (it, l)] = np.stack([m for _, m in order[l::per]])
+        out['step%d/out_masks' % it] = np.stack([m for _, m in order[n_layers::per]])
     out['losses'] = np.asarray(losses, dtype=np.float64)
     out['gnorms'] = np.asarray(norms, dtype=np.float64)
     for v in tf.trainable_variables():

@@ -167,7 +167,7 @@ def test_c2_mw_training_steps_match_oracle(cuda, exact, plan_agg):
             assert np.abs(got - want).max() <= utol * upd + 1e-7, (k, np.abs(got - want).max(), upd)
             acc_got = model.att_emb.accs[k].cpu().numpy().astype(np.float64).reshape(want.shape)
             acc_upd = np.abs(om.acc[k] - 0.1).max()
-            assert np.abs(acc_got - om.acc[k]).max() <= 2 * utol * acc_upd + 1e-9, (k, 'acc')
+            assert np.abs(acc_got - om.acc[k]).max() <= 2 * utol * acc_upd + 3e-8, (k, 'acc')      # fp32(0.1) is 1.5e-9 off
     finally:
         _lib.exact_fp32 = False
 

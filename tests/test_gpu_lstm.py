@@ -30,8 +30,12 @@ def _ref_lstm(X, W, b, keep, in_mask, out_mask):
 
 
 @pytest.mark.parametrize('exact', [True, False])
-@pytest.mark.parametrize('T,mb,d_in,H,keep', [(5, 16, 8, 8, 1.0), (7, 33, 12, 16, 0.5), (4, 130, 64, 64, 0.5)])
+@pytest.mark.parametrize('T,mb,d_in,H,keep', [(5, 16, 8, 8, 1.0), (7, 33, 12, 16, 0.5), (4, 130, 64, 64, 0.5),
+                                              (1, 40, 32, 32, 1.0), (6, 200, 32, 32, 0.5), (9, 300, 128, 128, 0.5),
+                                              (50, 512, 64, 64, 0.5), (12, 1024, 96, 128, 1.0)])
 def test_lstm_layer_forward_backward(cuda, T, mb, d_in, H, keep, exact):
+    """H in {32, 64, 128} on the tensor-core path runs the persistent cluster kernels (arx_lstm_seq_fwd / _bwd):
+    1, 2 and 4 CTAs per cluster, ragged last row tile, T = 1."""
     import arecsys_b200  # noqa: F401
     from arecsys_b200 import _lib
     from arecsys_b200.lstm.lstm_layer import LSTMLayer
@@ -53,6 +57,7 @@ def test_lstm_layer_forward_backward(cuda, T, mb, d_in, H, keep, exact):
     finally:
         _lib.exact_fp32 = False
     tol = 2e-5 if exact else 3e-3
+    assert bool(getattr(layer, '_seq', False)) == ((not exact) and H in (32, 64, 128)), 'persistent-kernel dispatch'
 
     def close(a, r, name):
         r = r.detach().numpy()
@@ -190,3 +195,29 @@ def test_seqmodel_ce_fused_tensor_core_path(cuda, use_concat, sep):
     finally:
         _lib.ce_fwd = orig
     assert len(calls) == 4, 'the fused CE path did not run'
+
+
+@pytest.mark.parametrize('T,mb,H', [(7, 260, 32), (20, 512, 64), (50, 4096, 128)])
+def test_lstm_persistent_kernels_match_per_step_kernels(cuda, T, mb, H, monkeypatch):
+    """The cluster kernels against the round-1 per-step path (one tcgen05 GEMM + one gate kernel per time step), both on
+    tf32 operands: same recurrence, so they agree far inside the parity bar — at the north-star shape too
+    (mb 4096, d = H = 128, T 50)."""
+    import arecsys_b200  # noqa: F401
+    from arecsys_b200.lstm.lstm_layer import LSTMLayer
+    rng = np.random.default_rng(T + mb)
+    d_in = H
+    X = torch.tensor(rng.standard_normal((T, mb, d_in)).astype(np.float32), device='cuda')
+    W = (rng.standard_normal((d_in + H, 4 * H)) * (1.0 / np.sqrt(d_in + H))).astype(np.float32)
+    b = (rng.standard_normal(4 * H) * 0.1).astype(np.float32)
+    dO = torch.tensor(rng.standard_normal((T, mb, H)).astype(np.float32), device='cuda')
+    res = []
+    for seq in ('1', '0'):
+        monkeypatch.setenv('ARX_LSTM_SEQ', seq)
+        layer = LSTMLayer(d_in, H, cuda, W=W, b=b)
+        out = layer.forward(X, 1.0)
+        dX = layer.backward(dO)
+        assert bool(layer._seq) == (seq == '1')
+        res.append((out.clone(), dX.clone(), layer.dW.clone(), layer.db.clone()))
+    for a, r, name in zip(res[0], res[1], ('out', 'dX', 'dW', 'db')):
+        err = float((a - r).abs().max() / r.abs().max().clamp_min(1e-6))
+        assert err < 2e-3, (name, err)

@@ -150,6 +150,7 @@ class SeqCase(object):
         self.d = d
         self.output_feat = int(d['output_feat']) if 'output_feat' in d.files else 1
         self.no_input_item_feature = bool(d['no_input_item_feature']) if 'no_input_item_feature' in d.files else False
+        self.num_layers = int(d['num_layers']) if 'num_layers' in d.files else 1
         self.loss = str(d['loss'])
         self.use_concat, self.sep, self.adagrad = bool(d['use_concat']), bool(d['sep']), bool(d['adagrad'])
         self.dim, self.mb, self.T = int(d['dim']), int(d['mb']), int(d['T'])
@@ -165,6 +166,12 @@ class SeqCase(object):
         self.i2l_d[self.START] = 0
         self.params = {k[len('init/'):]: d[k] for k in d.files if k.startswith('init/')}
         self.final = {k[len('final/'):]: d[k] for k in d.files if k.startswith('final/')}
+
+    def masks(self, it):
+        """(input masks of layer 0, output masks of the stack[, input masks of layer 1, ...]) of training step `it`."""
+        d = self.d
+        return (d['step%d/in_masks' % it], d['step%d/out_masks' % it]) + tuple(
+            d['step%d/in_masks_%d' % (it, l)] for l in range(1, self.num_layers))
 
     def batch(self, tag):
         d = self.d
@@ -399,11 +406,12 @@ def test_oracle_reproduces_reference_lstm_run_nondefault_flags(name):
     ref = TorchRefSeq(c.ua, c.ia, {k: v.copy() for k, v in c.params.items()}, c.l2i_d, c.i2l_d, loss=c.loss,
                       keep_prob=c.keep, learning_rate=c.lr, n_sampled=None, dtype=torch.float64, size=c.dim,
                       use_concat=c.use_concat, no_user_id=False, max_gradient_norm=c.clip, item_output=c.sep,
-                      withAdagrad=c.adagrad, output_feat=c.output_feat, no_input_item_feature=c.no_input_item_feature)
+                      withAdagrad=c.adagrad, output_feat=c.output_feat, no_input_item_feature=c.no_input_item_feature,
+                      num_layers=c.num_layers)
     for it in range(c.n_steps):
         users, inp, tgt, w, pos = c.batch('step%d' % it)
         ref.pos, ref.pos_eval = pos, pos
-        l = ref.step_seq(users, inp, tgt, w, masks=(c.d['step%d/in_masks' % it], c.d['step%d/out_masks' % it]))
+        l = ref.step_seq(users, inp, tgt, w, masks=c.masks(it))
         want = float(c.d['losses'][it])
         assert abs(l - want) <= 2e-5 * max(1.0, abs(want)), (name, it, l, want)
         gn = float(c.d['gnorms'][it])
@@ -430,16 +438,15 @@ def test_cuda_path_reproduces_reference_lstm_run_nondefault_flags(cuda, name):
     try:
         params = {k: v.copy() for k, v in c.params.items()}
         emb = EmbeddingAttribute(c.ua, c.ia, c.mb, None, c.T, c.sep, c.i2l_d, c.l2i_d, params=params)
-        model = SeqModel(c.buckets, c.dim, 1, c.clip, c.mb, c.lr, 0.83, emb, withAdagrad=c.adagrad,
+        model = SeqModel(c.buckets, c.dim, c.num_layers, c.clip, c.mb, c.lr, 0.83, emb, withAdagrad=c.adagrad,
                          dropoutRate=c.keep, START_ID=c.START, loss=c.loss, use_concat=c.use_concat,
                          no_user_id=False, topk_n=c.topk, params=params, output_feat=c.output_feat,
                          no_input_item_feature=c.no_input_item_feature)
         for it in range(c.n_steps):
             users, inp, tgt, w, pos = c.batch('step%d' % it)
             emb.prepare_warp(pos, pos)
-            im = torch.tensor(c.d['step%d/in_masks' % it], device='cuda')
-            om = torch.tensor(c.d['step%d/out_masks' % it], device='cuda')
-            l = model.step(None, users, inp, tgt, w, int(c.d['step%d/bucket' % it]), masks=(im, om))
+            l = model.step(None, users, inp, tgt, w, int(c.d['step%d/bucket' % it]),
+                           masks=tuple(torch.tensor(m, device='cuda') for m in c.masks(it)))
             want = float(c.d['losses'][it])
             assert abs(l - want) <= 2e-4 * max(1.0, abs(want)), (name, it, l, want)
         dense = model.dense_params()

@@ -24,6 +24,12 @@ class AttrDesc(ctypes.Structure):
                 ('lengths_full', vp)]
 
 
+class PoolReq(ctypes.Structure):
+    """arx_pool_req (include/arx_b200.h)."""
+    _fields_ = [('attrs', vp), ('ent_ids', vp), ('out', vp), ('bias_out', vp), ('n', ctypes.c_int64),
+                ('out_stride', ctypes.c_int64), ('n_attr', ctypes.c_int32), ('max_rows_per_entity', ctypes.c_int32)]
+
+
 class BwdPlan(ctypes.Structure):
     """arx_bwd_plan (include/arx_b200.h)."""
     _fields_ = [('counters', vp), ('uniq_tok', vp), ('uniq_attr', vp), ('row_base', vp),
@@ -67,6 +73,9 @@ SIGNATURES = {
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_lstm_gates_fwd2': [vp, vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd2': [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp],
+    'arx_pool_fwd_many': [vp, i32, i32, vp],
+    'arx_mw_prep': [vp, vp, f32, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
+    'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp],
     'arx_lstm_seq_fwd': [vp, vp, vp, vp, i64, i64, i32, f32, vp],
     'arx_lstm_seq_bwd': [vp, vp, vp, vp, i64, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],
@@ -148,7 +157,7 @@ def call(name, *args):
 
 
 _MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd', 'arx_lstm_seq_fwd',
-                       'arx_lstm_seq_bwd')
+                       'arx_lstm_seq_bwd', 'arx_pool_fwd_many', 'arx_mw_prep', 'arx_mw_post')
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 
@@ -259,13 +268,16 @@ def mw_fwd(U_r, P_r, beta, tscore, mask, mask_ld, M, N, d):
     return hsum, loss
 
 
-def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None):
-    """(dU, dP, dbeta, dts) of sum_r g[r] * loss[r]."""
+def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=None, PT=None):
+    """(dU, dP, dbeta, dts) of sum_r g[r] * loss[r].  UT / PT: the transposed operands when the caller already has
+    them (arx_mw_prep emits them with the rounding pass)."""
     dev = U_r.device
-    UT = torch.empty((d, M), dtype=torch.float32, device=dev)
-    PT = torch.empty((d, N), dtype=torch.float32, device=dev)
-    call('arx_transpose', U_r.data_ptr(), M, d, UT.data_ptr(), 0)
-    call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
+    if UT is None:
+        UT = torch.empty((d, M), dtype=torch.float32, device=dev)
+        call('arx_transpose', U_r.data_ptr(), M, d, UT.data_ptr(), 0)
+    if PT is None:
+        PT = torch.empty((d, N), dtype=torch.float32, device=dev)
+        call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
     dU = torch.empty((M, d), dtype=torch.float32, device=dev)
     if dP is None:
         dP = torch.empty((N, d), dtype=torch.float32, device=dev)

@@ -435,21 +435,35 @@ class EmbeddingAttribute(object):
             return None
         return loss, grads
 
-    def fused_mw(self, latent, Ps, bs, tscore, row_scale, want_grad, forward_only=False, pos_rows=None, dP=None):
-        """Sampled-pool scoring (:148-206, pool='sampled') + _compute_mw_loss (:641-649) + their gradients on the
-        tensor cores without writing the [rows, S] scores: arx_mw_mask_build / arx_mw_fwd / arx_mw_bwd.
-        Returns (loss_rows, (dU, dPs, dbs, dts) or None), or None when the shape is not supported."""
-        M, d, S = latent.shape[0], self.dim, Ps.shape[0]
-        if not _lib.ce_supported(M, S, d):
-            return None
+    def mw_mask(self, M, S, forward_only=False, pos_rows=None):
+        """Bit matrix of the positives that sit in the sampled pool (arx_mw_mask_build): depends on the batch's user ids
+        and the pool only, so the step builds it on a side stream under the lookups."""
         key = 'mw' + ('_eval' if forward_only else '_train')
         pos_ptr, pos_idx = self._positives(key)
         pos_row = pos_rows if pos_rows is not None else self.u_indices['input']
         ld = _lib.mw_mask_words(S)
         mask = torch.empty((M, ld), dtype=torch.int32, device=self.device)
         call('arx_mw_mask_build', pos_row.data_ptr(), pos_ptr.data_ptr(), pos_idx.data_ptr(), M, S, mask.data_ptr(), ld)
-        U_r = _lib.round_tf32(latent if latent.is_contiguous() else latent.contiguous())
-        P_r = _lib.round_tf32(Ps)
+        return mask, ld
+
+    def fused_mw(self, latent, Ps, bs, tscore, row_scale, want_grad, forward_only=False, pos_rows=None, dP=None,
+                 prepared=None, mask=None):
+        """Sampled-pool scoring (:148-206, pool='sampled') + _compute_mw_loss (:641-649) + their gradients on the
+        tensor cores without writing the [rows, S] scores: arx_mw_mask_build / arx_mw_fwd / arx_mw_bwd.
+        Returns (loss_rows, (dU, dPs, dbs, dts) or None), or None when the shape is not supported."""
+        M, d, S = latent.shape[0], self.dim, Ps.shape[0]
+        if not _lib.ce_supported(M, S, d):
+            return None
+        if mask is None:
+            mask, ld = self.mw_mask(M, S, forward_only, pos_rows)
+        else:
+            mask, ld = mask
+        UT = PT = None
+        if prepared is not None:               # arx_mw_prep already rounded / transposed the operands
+            U_r, P_r, UT, PT = prepared
+        else:
+            U_r = _lib.round_tf32(latent if latent.is_contiguous() else latent.contiguous())
+            P_r = _lib.round_tf32(Ps)
         fw = _lib.mw_fwd(U_r, P_r, bs, tscore, mask, ld, M, S, d)
         if fw is None:
             return None
@@ -457,7 +471,7 @@ class EmbeddingAttribute(object):
         if not want_grad:
             return loss, None
         g = row_scale if row_scale is not None else torch.ones(M, dtype=torch.float32, device=self.device)
-        grads = _lib.mw_bwd(U_r, P_r, bs, tscore, mask, ld, hsum, g, M, S, d, dP=dP)
+        grads = _lib.mw_bwd(U_r, P_r, bs, tscore, mask, ld, hsum, g, M, S, d, dP=dP, UT=UT, PT=PT)
         if grads is None:
             return None
         return loss, grads
@@ -673,6 +687,16 @@ class EmbeddingAttribute(object):
         plan = _Plan(self.device, cap_rows, cap_occ, self.dim) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
         _lib.tag = ts.prefix
         _lib.load().arx_set_tuning(b'plan_agg', self.plan_agg)     # host-side launch-shape choice of THIS model
+        # consecutive lookups over the same attribute range and mode (the sampled pool and the target items of an
+        # `mw` step) are walked as ONE id list: their arena rows are consecutive in the same order
+        merged = []
+        for sp in specs:
+            if merged and merged[-1][0] == sp[0] and merged[-1][1] == sp[1] and merged[-1][3] == sp[3]:
+                merged[-1] = (sp[0], sp[1], merged[-1][2] + [sp[2]], sp[3])
+            else:
+                merged.append((sp[0], sp[1], [sp[2]], sp[3]))
+        specs = [(a0, na, (l[0] if len(l) == 1 else torch.cat(l)), mode) for (a0, na, l, mode) in merged]
+        plan._keep = specs                                  # the concatenated id lists live as long as the plan
         call('arx_bwd_plan_begin', plan.c)
         for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
@@ -837,6 +861,23 @@ class EmbeddingAttribute(object):
             width = self.dim if mode == POOL_MEAN else self.dim * na
             outs.append((torch.empty((ids.numel(), width), dtype=torch.float32, device=self.device),
                          torch.empty((ids.numel(),), dtype=torch.float32, device=self.device) if want_bias else None))
+        if (len(requests) > 1 and len(requests) <= 4 and self.dim in (128, 256)
+                and all(r[2] == POOL_MEAN for r in requests) and os.environ.get('ARX_POOL_MANY', '1') == '1'):
+            # all lookups of the step in ONE launch (arx_pool_fwd_many): one ramp, one tail, balanced waves
+            reqs = (_lib.PoolReq * len(requests))()
+            rngs = []
+            for k, ((prefix, ids, mode, want_bias, kw), (o, b)) in enumerate(zip(requests, outs)):
+                ts = self.sets[prefix]
+                a0, na = ts.attr_range(kw.get('no_id', False), kw.get('no_attribute', False))
+                rngs.append((a0, na))
+                q = reqs[k]
+                q.attrs, q.ent_ids, q.out = ts.desc_ptr(a0), ids.data_ptr(), o.data_ptr()
+                q.bias_out = b.data_ptr() if want_bias else None
+                q.n, q.out_stride, q.n_attr = ids.numel(), o.stride(0), na
+                q.max_rows_per_entity = int(sum(ts.max_len[a0:a0 + na]))
+            _lib.tag = 'many'
+            if call('arx_pool_fwd_many', ctypes.addressof(reqs), len(requests), self.dim) == 0:
+                return [(o, b, rg) for (o, b), rg in zip(outs, rngs)]
         res, forks = [], []
         for k, ((prefix, ids, mode, want_bias, kw), (o, b)) in enumerate(zip(requests, outs)):
             side = self.side_stream(k) if (k > 0 and _lib.timeline is None) else None

@@ -59,6 +59,16 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Explicit shared-space accesses: through a generic pointer the compiler emits LD.E / ST.E, which take the slow
+// generic path and are NOT ordered with a following mbarrier arrive by the shared-memory pipeline.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -196,17 +206,15 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       // x-projection (+ bias) of my 4 x 16 gate columns from the TMA-staged, 128-byte-swizzled tile
       float z[4][16];
       mbar_wait(smem_u32(&zx_full), (uint32_t)t & 1u);
+      const uint32_t zrow0 = smem_u32(sZ) + (uint32_t)rt * 128u;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const uint8_t* zrow = sZ + g * LS_SLAB + rt * 128;
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 v = *reinterpret_cast<const float4*>(zrow + (((uh * 4 + c4) ^ (rt & 7)) << 4));
+          const float4 v = lds_f4(zrow0 + (uint32_t)g * LS_SLAB + (uint32_t)(((uh * 4 + c4) ^ (rt & 7)) << 4));
           z[g][c4 * 4] = v.x; z[g][c4 * 4 + 1] = v.y; z[g][c4 * 4 + 2] = v.z; z[g][c4 * 4 + 3] = v.w;
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&zx_empty));       // the producer may stage step t + 1
       if (t > 0) {
         mbar_wait(smem_u32(&acc_full), (uint32_t)(t - 1) & 1u);
         tc_fence_after();
@@ -218,7 +226,17 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
           for (int i = 0; i < 16; ++i) z[g][i] += a[i];
         }
         tc_fence_before();
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) z[g][i] += 0.f * z[g][i];      // consume the staged values (see below)
       }
+      // Release the staging tile only AFTER every staged value has been consumed by an arithmetic instruction: a load
+      // that is merely issued may still be in flight when the arrive executes, and the TMA write of step t + 1 then
+      // overtakes it (seen on hardware as a rare wrong 16-byte chunk of one gate).
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&zx_empty));       // the producer may stage step t + 1
       float h[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -397,10 +415,10 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
           mbar_wait_cluster(smem_u32(&recv_full[buf]), (uint32_t)((it - 1) >> 1) & 1u);
 #pragma unroll
           for (int s = 0; s < NC - 1; ++s) {                               // fixed sender order: deterministic
-            const float* src = sR + ((size_t)(buf * (NC - 1) + s) * LS_BM + rt) * LS_UC + uh * 16;
+            const uint32_t src = smem_u32(sR + ((size_t)(buf * (NC - 1) + s) * LS_BM + rt) * LS_UC + uh * 16);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4) {
-              const float4 v = *reinterpret_cast<const float4*>(src + c4 * 4);
+              const float4 v = lds_f4(src + c4 * 16);
               dh[c4 * 4] += v.x; dh[c4 * 4 + 1] += v.y; dh[c4 * 4 + 2] += v.z; dh[c4 * 4 + 3] += v.w;
             }
           }
@@ -454,11 +472,11 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
         // my dZ columns -> the A tile (k block = gate g, chunks uh*4 ..): the previous MMA has retired (acc_full waited)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint8_t* arow = sA + g * LS_SLAB + rt * 128;
+          const uint32_t arow = smem_u32(sA + g * LS_SLAB + rt * 128);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4)
-            *reinterpret_cast<float4*>(arow + (((uh * 4 + c4) ^ (rt & 7)) << 4)) =
-                make_float4(dz[g][c4 * 4], dz[g][c4 * 4 + 1], dz[g][c4 * 4 + 2], dz[g][c4 * 4 + 3]);
+            sts_f4(arow + (uint32_t)(((uh * 4 + c4) ^ (rt & 7)) << 4),
+                   make_float4(dz[g][c4 * 4], dz[g][c4 * 4 + 1], dz[g][c4 * 4 + 2], dz[g][c4 * 4 + 3]));
         }
         fence_async_proxy();
         tc_fence_before();
@@ -547,7 +565,7 @@ extern "C" int arx_lstm_seq_fwd(float* G, const float* WhT, float* Hs, float* Cs
   CUtensorMap mw, mz;
   if (!make_map(&mw, WhT, 4ll * H, H, 32)) return ARX_E_UNSUPPORTED;
   if (!make_map(&mz, G, T * mb, 4ll * H, LS_BM)) return ARX_E_UNSUPPORTED;
-  LstmSeqParams p{G, Hs, Cs, nullptr, nullptr, (long long)mb, (int)T, forget_bias, 1};
+  LstmSeqParams p{G, Hs, Cs, nullptr, nullptr, (long long)mb, (int)T, forget_bias, 0};
   cudaStream_t st = (cudaStream_t)stream;
   if (H == 32) return launch_fwd<1>(mw, mz, p, st);
   if (H == 64) return launch_fwd<2>(mw, mz, p, st);

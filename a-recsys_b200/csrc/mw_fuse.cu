@@ -1,0 +1,112 @@
+// Small fused kernels around the sampled-WMRB tensor-core kernels (arx_mw_fwd / arx_mw_bwd) of the HMF `mw` step
+// (hmf/hmf_model.py:78,112-115 + embed_attribute.py:208-220,236): the dependent chain between the lookups and the
+// scatter-Adagrad was 12 launches of 3-15 us each; these two replace eight of them.
+//   arx_mw_prep : u = dropout(u0) ; U_r = tf32(u) ; UT = U_r^T ; tscore = u . Pt + bt ; P_r = tf32(Ps) ; PT = P_r^T
+//                 (was arx_scale_mask + 2 x arx_round_tf32 + 2 x arx_transpose + arx_rowdot_fwd)
+//   arx_mw_post : du0 = (dU + dts * Pt) * mask / keep ; dPt = dts * u
+//                 (was arx_rowdot_bwd + arx_scale_mask)
+#include "arx_common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float tf32_round(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+constexpr int kPrepRows = 32;
+
+// grid: ceil(M / 32) blocks for the batch rows, then ceil(S / 32) blocks for the pool rows; 256 threads
+__global__ void __launch_bounds__(256)
+mw_prep_kernel(const float* __restrict__ u0, const float* __restrict__ mask, float inv_keep,
+               const float* __restrict__ Pt, const float* __restrict__ bt, const float* __restrict__ Ps,
+               long long M, long long S, int d, float* __restrict__ u, float* __restrict__ U_r,
+               float* __restrict__ UT, float* __restrict__ tscore, float* __restrict__ P_r, float* __restrict__ PT) {
+  extern __shared__ float tile[];                       // [32][d + 1]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long ublocks = (M + kPrepRows - 1) / kPrepRows;
+  const bool is_u = (long long)blockIdx.x < ublocks;
+  const long long row0 = (is_u ? (long long)blockIdx.x : (long long)blockIdx.x - ublocks) * kPrepRows;
+  const long long R = is_u ? M : S;
+  const float* __restrict__ src = is_u ? u0 : Ps;
+  float* __restrict__ dst_r = is_u ? U_r : P_r;
+  float* __restrict__ dst_t = is_u ? UT : PT;
+  const int ld = d + 1;
+  for (int r = warp; r < kPrepRows; r += 8) {
+    const long long row = row0 + r;
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float x = 0.f;
+      if (row < R) {
+        x = __ldg(src + row * d + c);
+        if (is_u) {
+          if (mask != nullptr) x = x * inv_keep * __ldg(mask + row * d + c);      // tf.nn.dropout: x / keep * mask
+          u[row * d + c] = x;
+          if (Pt != nullptr) dot = fmaf(x, __ldg(Pt + row * d + c), dot);
+        }
+        const float xr = tf32_round(x);
+        dst_r[row * d + c] = xr;
+        x = xr;
+      }
+      tile[r * ld + c] = x;
+    }
+    if (is_u && tscore != nullptr) {
+      dot = warp_sum(dot);
+      if (lane == 0 && row < R) tscore[row] = dot + (bt != nullptr ? __ldg(bt + row) : 0.f);   // :220
+    }
+  }
+  __syncthreads();
+  const long long row = row0 + lane;
+  if (dst_t != nullptr && row < R)
+    for (int c = warp; c < d; c += 8) dst_t[(long long)c * R + row] = tile[lane * ld + c];
+}
+
+__global__ void __launch_bounds__(256)
+mw_post_kernel(const float* __restrict__ dU, const float* __restrict__ dts, const float* __restrict__ Pt,
+               const float* __restrict__ u, const float* __restrict__ mask, float inv_keep, long long n, int d,
+               float* __restrict__ du0, float* __restrict__ dPt) {
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    const float g = __ldg(dts + i / d);
+    const float4 a = ld_f4(dU + i), p = ldg_f4(Pt + i), uu = ldg_f4(u + i);
+    float4 o = make_float4(fmaf(g, p.x, a.x), fmaf(g, p.y, a.y), fmaf(g, p.z, a.z), fmaf(g, p.w, a.w));
+    if (mask != nullptr) {
+      const float4 m = ldg_f4(mask + i);
+      o = make_float4(o.x * inv_keep * m.x, o.y * inv_keep * m.y, o.z * inv_keep * m.z, o.w * inv_keep * m.w);
+    }
+    st_f4(du0 + i, o);
+    st_f4(dPt + i, make_float4(g * uu.x, g * uu.y, g * uu.z, g * uu.w));
+  }
+}
+
+}  // namespace
+
+extern "C" int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const float* Pt, const float* bt,
+                           const float* Ps, int64_t M, int64_t S, int d, float* u, float* U_r, float* UT,
+                           float* tscore, float* P_r, float* PT, void* stream) {
+  if (!u0 || !u || !U_r || M < 0 || S < 0 || d < 1 || (S > 0 && (!Ps || !P_r))) return ARX_E_BADARG;
+  if (M == 0 && S == 0) return ARX_OK;
+  const size_t smem = (size_t)kPrepRows * (d + 1) * sizeof(float);
+  if (smem > 48 * 1024) return ARX_E_UNSUPPORTED;
+  const long long blocks = (M + kPrepRows - 1) / kPrepRows + (S + kPrepRows - 1) / kPrepRows;
+  mw_prep_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(u0, mask, inv_keep, Pt, bt, Ps, (long long)M,
+                                                                       (long long)S, d, u, U_r, UT, tscore, P_r, PT);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+extern "C" int arx_mw_post(const float* dU, const float* dts, const float* Pt, const float* u, const float* mask,
+                           float inv_keep, int64_t M, int d, float* du0, float* dPt, void* stream) {
+  if (!dU || !dts || !Pt || !u || !du0 || !dPt || M < 0 || d < 1) return ARX_E_BADARG;
+  if (M == 0) return ARX_OK;
+  if ((d % 4) || ((uintptr_t)dU & 15) || ((uintptr_t)Pt & 15) || ((uintptr_t)u & 15) || ((uintptr_t)du0 & 15) ||
+      ((uintptr_t)dPt & 15) || (mask && ((uintptr_t)mask & 15)))
+    return ARX_E_UNSUPPORTED;
+  const long long n = (long long)M * d;
+  const long long b = (n / 4 + 255) / 256;
+  const int grid = (int)std::min<long long>(std::max<long long>(b, 1), (long long)arx_num_sms() * 8);
+  mw_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dU, dts, Pt, u, mask, inv_keep, n, d, du0, dPt);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}

@@ -216,10 +216,10 @@ constexpr int kFlatRows = 1024;
 constexpr int kFlatU = 8;
 
 template <int CPL>      // float4 columns per lane: dim = 128 * CPL
-__global__ void __launch_bounds__(256, CPL == 1 ? 4 : 2)
-pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
-                     long long n, float* __restrict__ out, long long out_stride,
-                     float* __restrict__ bias_out, int epb) {
+__device__ __forceinline__ void
+pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
+                   long long n, float* __restrict__ out, long long out_stride,
+                   float* __restrict__ bias_out, int epb, long long vblock, long long vgrid) {
   constexpr int dim = 128 * CPL;
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_off[kFlatBags + 1];
@@ -237,7 +237,7 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
   const float Ff = (float)n_attr;
   const bool want_bias = bias_out != nullptr;
 
-  for (long long g0 = (long long)blockIdx.x * epb; g0 < n; g0 += (long long)gridDim.x * epb) {
+  for (long long g0 = vblock * epb; g0 < n; g0 += vgrid * epb) {
    const int ng = (int)min((long long)epb, n - g0);
    for (int first = 0; first < ng;) {                 // sub-groups that fit kFlatRows rows
     const long long e0 = g0 + first;
@@ -371,6 +371,41 @@ pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, cons
     __syncthreads();
    }
   }
+}
+
+template <int CPL>
+__global__ void __launch_bounds__(256, CPL == 1 ? 4 : 2)
+pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
+                     long long n, float* __restrict__ out, long long out_stride,
+                     float* __restrict__ bias_out, int epb) {
+  pool_fwd_flat_body<CPL>(g_attrs, n_attr, ids, n, out, out_stride, bias_out, epb, blockIdx.x, gridDim.x);
+}
+
+// Several independent lookups (e.g. the users, the target items and the sampled pool of one training step) in ONE
+// launch: each request owns a contiguous range of CTAs.  One launch ramp and one tail instead of one per lookup, and
+// the CTAs of a short lookup fill the slots the long one leaves free.
+constexpr int kManyReqs = 4;
+struct PoolManyParams {
+  const arx_attr_desc* attrs[kManyReqs];
+  const int* ids[kManyReqs];
+  float* out[kManyReqs];
+  float* bias_out[kManyReqs];
+  long long n[kManyReqs];
+  long long out_stride[kManyReqs];
+  int n_attr[kManyReqs];
+  int epb[kManyReqs];
+  int block_end[kManyReqs];        // exclusive prefix of CTAs per request
+  int n_req;
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(256, CPL == 1 ? 4 : 2)
+pool_fwd_flat_many_kernel(const PoolManyParams mp) {
+  int r = 0;
+  while (r + 1 < mp.n_req && (int)blockIdx.x >= mp.block_end[r]) ++r;
+  const int b0 = r == 0 ? 0 : mp.block_end[r - 1];
+  pool_fwd_flat_body<CPL>(mp.attrs[r], mp.n_attr[r], mp.ids[r], mp.n[r], mp.out[r], mp.out_stride[r], mp.bias_out[r],
+                          mp.epb[r], (long long)blockIdx.x - b0, (long long)(mp.block_end[r] - b0));
 }
 
 // integer part of K2 (mulhot_index.py:48-67)
@@ -1020,12 +1055,14 @@ int launch_fwd(const arx_attr_desc* attrs, int n_attr, int dim, const int32_t* i
     long long blocks = (n + epb - 1) / epb;
     const long long cap = slots * 4;
     const int grid = (int)(blocks > cap ? cap : blocks);
-    static bool cfg1 = false, cfg2 = false;
+    // the dynamic size grows with the attribute count: raise the opt-in limit whenever a larger request comes
+    // (configuring once with the FIRST request's size made later, wider table sets fail to launch)
+    static size_t cfg1 = 0, cfg2 = 0;
     if (dim == 128) {
-      if (!cfg1) { cudaFuncSetAttribute(pool_fwd_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = true; }
+      if (smem > cfg1) { cudaFuncSetAttribute(pool_fwd_flat_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = smem; }
       pool_fwd_flat_kernel<1><<<grid, threads, smem, st>>>(attrs, n_attr, ids, (long long)n, out, (long long)out_stride, bias_out, epb);
     } else {
-      if (!cfg2) { cudaFuncSetAttribute(pool_fwd_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg2 = true; }
+      if (smem > cfg2) { cudaFuncSetAttribute(pool_fwd_flat_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg2 = smem; }
       pool_fwd_flat_kernel<2><<<grid, threads, smem, st>>>(attrs, n_attr, ids, (long long)n, out, (long long)out_stride, bias_out, epb);
     }
     ARX_CHECK_LAUNCH();
@@ -1067,6 +1104,56 @@ extern "C" int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim, con
   const bool v4 = (dim % 4 == 0) && (out_stride % 4 == 0) && (((uintptr_t)out & 15) == 0);
   return v4 ? launch_fwd<4>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, max_rows_per_entity, st)
             : launch_fwd<1>(attrs, n_attr, dim, ent_ids, n, out, out_stride, mode, bias_out, 0, st);
+}
+
+// K1+K2 for several independent lookups in one launch (mean mode, dim 128 / 256, every request within the flat
+// kernel's limits); ARX_E_UNSUPPORTED otherwise: the caller then issues one arx_pool_fwd per lookup.
+extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream) {
+  if (!reqs || n_req < 1 || n_req > kManyReqs) return ARX_E_BADARG;
+  if (dim != 128 && dim != 256) return ARX_E_UNSUPPORTED;
+  PoolManyParams mp{};
+  const int cps = (dim == 128) ? 4 : 2;
+  const long long slots = (long long)arx_num_sms() * cps;
+  long long total_n = 0;
+  int max_attr = 0, k = 0;
+  for (int i = 0; i < n_req; ++i) {
+    const arx_pool_req& q = reqs[i];
+    if (!q.attrs || !q.ent_ids || !q.out || q.n_attr < 1 || q.n_attr > kMaxAttr || q.n < 0) return ARX_E_BADARG;
+    if (q.n_attr > kFlatBags || q.max_rows_per_entity <= 0 || q.max_rows_per_entity > kFlatRows || (q.out_stride % 4) ||
+        ((uintptr_t)q.out & 15))
+      return ARX_E_UNSUPPORTED;
+    total_n += q.n;
+    max_attr = std::max(max_attr, q.n_attr);
+  }
+  if (total_n == 0) return ARX_OK;
+  int blocks = 0;
+  for (int i = 0; i < n_req; ++i) {
+    const arx_pool_req& q = reqs[i];
+    if (q.n == 0) continue;
+    int epb = std::min(kFlatBags / q.n_attr, kFlatEnt);
+    // entities per CTA: as many as fit, but not more than what spreads the whole batch of lookups over one wave
+    const int even = (int)((total_n + slots - 1) / slots);
+    if (even >= 1 && even < epb) epb = even;
+    if (g_tune_flat_epb > 0 && g_tune_flat_epb < epb) epb = g_tune_flat_epb;
+    mp.attrs[k] = q.attrs; mp.ids[k] = q.ent_ids; mp.out[k] = q.out; mp.bias_out[k] = q.bias_out;
+    mp.n[k] = q.n; mp.out_stride[k] = q.out_stride; mp.n_attr[k] = q.n_attr; mp.epb[k] = epb;
+    blocks += (int)std::min<long long>((q.n + epb - 1) / epb, slots * 4);
+    mp.block_end[k] = blocks;
+    ++k;
+  }
+  mp.n_req = k;
+  const size_t smem = (size_t)(kFlatEnt + 16) * dim * 4 + (size_t)kFlatRows * (8 + 8) + (size_t)max_attr * sizeof(arx_attr_desc);
+  cudaStream_t st = (cudaStream_t)stream;
+  static size_t cfg1 = 0, cfg2 = 0;
+  if (dim == 128) {
+    if (smem > cfg1) { cudaFuncSetAttribute(pool_fwd_flat_many_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg1 = smem; }
+    pool_fwd_flat_many_kernel<1><<<blocks, 256, smem, st>>>(mp);
+  } else {
+    if (smem > cfg2) { cudaFuncSetAttribute(pool_fwd_flat_many_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg2 = smem; }
+    pool_fwd_flat_many_kernel<2><<<blocks, 256, smem, st>>>(mp);
+  }
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
 }
 
 extern "C" int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const int32_t* ent_ids,

@@ -368,8 +368,11 @@ ce_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUt
         if (row < R) {
           float* dst = p.out + (size_t)row * p.d + cc * 32;
           if (p.atomic_out) {
+            // split accumulation: 128-bit vector reductions (one L2 atomic per 16 bytes instead of one per float)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(dst + i, a[i]);
+            for (int i = 0; i < 32; i += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(a[i]), "f"(a[i + 1]),
+                           "f"(a[i + 2]), "f"(a[i + 3]) : "memory");
           } else {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(a[i], a[i + 1], a[i + 2], a[i + 3]);

@@ -262,7 +262,25 @@ class LatentProductModel(object):
                                   pre: [(irng, sids, POOL_MEAN), (irng, item_ids, POOL_MEAN)]})
             if train and early:
                 plans()
-            if train and not masks:
+            S = sids.numel()
+            fast = (train and _lib.ce_supported(mb, S, self.size) and self.size % 4 == 0
+                    and os.environ.get('ARX_MW_FUSED_GLUE', '1') == '1')
+            main = torch.cuda.current_stream()
+            dmask = mwmask = None
+            ev_side = None
+            if fast:
+                # nothing below depends on the lookups: the dropout mask draw and the positives bit matrix are built
+                # on a side stream UNDER the lookups instead of on the dependent chain behind them
+                side = m.side_stream(3)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    if keep_prob != 1.0:
+                        dmask = masks[0] if masks else torch.floor(
+                            torch.rand((mb, self.size), dtype=torch.float32, device=self.device) + keep_prob)
+                    mwmask = m.mw_mask(mb, S)
+                    ev_side = torch.cuda.Event()
+                    ev_side.record(side)
+            elif train and not masks:
                 m.premake_dropout_mask((mb, self.size), keep_prob)
             (u0, _, urng), (Ps, bs, _), (Pt, bt, _) = m.pool_many([
                 ('user', m.u_indices['input'], POOL_MEAN, False, {}),
@@ -275,6 +293,46 @@ class LatentProductModel(object):
                 # latency-bound plan kernels (thousands of small CTAs) would take those slots.
                 plans()
             m._last_user = ('user', urng, m.u_indices['input'], POOL_MEAN)
+            if fast:
+                # ---- fused glue: dropout + tf32 rounding + transposes + target score in one launch (arx_mw_prep),
+                #      target-score adjoint + dropout adjoint in one (arx_mw_post) -------------------------------
+                dev = self.device
+                f32 = dict(dtype=torch.float32, device=dev)
+                main.wait_event(ev_side)
+                d = self.size
+                u = torch.empty((mb, d), **f32); U_r = torch.empty((mb, d), **f32); UT = torch.empty((d, mb), **f32)
+                P_r = torch.empty((S, d), **f32); PT = torch.empty((d, S), **f32)
+                tscore = torch.empty((mb,), **f32)
+                inv_keep = 1.0 / keep_prob
+                call('arx_mw_prep', u0.data_ptr(), ptr(dmask), inv_keep, Pt.data_ptr(), bt.data_ptr(), Ps.data_ptr(),
+                     mb, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), tscore.data_ptr(), P_r.data_ptr(),
+                     PT.data_ptr())                                            # :78 / embed :236, :115
+                arena = torch.empty((S + mb, d), **f32)
+                dPt = arena[S:]                   # both item-side gradients land in one arena: no concat
+                fused = m.fused_mw(u, Ps, bs, tscore, scale, True, dP=arena[:S], prepared=(U_r, P_r, UT, PT),
+                                   mask=mwmask)
+                if fused is None:
+                    raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
+                batch_loss, (dU, dPs, dbs, dts) = fused
+                du0 = torch.empty((mb, d), **f32)
+                call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), ptr(dmask), inv_keep,
+                     mb, d, du0.data_ptr(), dPt.data_ptr())
+                rng = m.sets[pre].attr_range()
+                m.push_grad(pre, rng, sids, POOL_MEAN, dPs, dbs)
+                m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)
+                m.push_grad('user', urng, m.u_indices['input'], POOL_MEAN, du0)
+                # the scalar loss is off the dependent chain: reduce it on the side stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    loss_val = batch_loss.mean()                               # :140
+                    ev_loss = torch.cuda.Event()
+                    ev_loss.record(side)
+                lr = self.learning_rate.eval()
+                m.apply_gradients(lr, OPT_ADAGRAD)                             # :146-151
+                main.wait_event(ev_loss)
+                self.global_step.assign(self.global_step.eval() + 1)
+                self.batch_loss = batch_loss
+                return float(loss_val.item()) if sync else loss_val
             u = m.dropout(u0, keep_prob, masks[0] if masks else None)          # :78 / embed :236
             ctx = ('linear', m._last_user, keep_prob, getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None)
             S = Ps.shape[0]

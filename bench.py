@@ -390,7 +390,7 @@ def main():
     # ---------------- per-kernel durations and roofline -----------------------------------
     agg = {}
     for name, tag, s0, s1 in tl:
-        k = '%s:%s' % (name, tag) if name in ('arx_pool_fwd', 'arx_pool_bwd_apply') else name
+        k = '%s:%s' % (name, tag) if name in ('arx_pool_fwd', 'arx_pool_bwd_apply', 'arx_pool_fwd_many') else name
         d = agg.setdefault(k, [0.0, 0])
         d[0] += s0.elapsed_time(s1)
         d[1] += 1
@@ -420,6 +420,9 @@ def main():
         if a.loss == 'mw' and model.att_emb.sampled_ids is not None:
             pool_ids = model.att_emb.sampled_ids.cpu().numpy().astype(np.int64)
             ib2 = algorithmic_bytes(ia, np.concatenate([pool_ids, item_ids.astype(np.int64)]), a.dim, True)
+            # the three lookups of the step (users, pool, targets) run as ONE launch (arx_pool_fwd_many)
+            roof('arx_pool_fwd_many:many', ub['fwd_unique'] + ib2['fwd_unique'], ub['fwd_nominal'] + ib2['fwd_nominal'],
+                 'pool_fwd_flat_many_kernel<1>: users + sampled pool + target items, %d entities' % (2 * a.mb + len(pool_ids)))
             roof('arx_pool_bwd_apply:item', ib2['bwd_unique'], ib2['bwd_nominal'],
                  'pool_bwd_apply_kernel<4> item side (pool + targets, %d entity rows)' % (len(pool_ids) + len(item_ids)))
             # whole step against the HBM roofline: embedding forward + backward bytes of both sides,

@@ -71,6 +71,21 @@ int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim,
                                             unknown: enables the flat row-list kernel when <= 1024 */,
                  void* stream);
 
+/* Several independent K1+K2 lookups of one step (users, target items, sampled pool: embed_attribute.py:222-254,
+ * :208-220, :479-508 are three separate sub-graphs in the reference) in ONE launch; mean mode, dim 128 / 256.
+ * ARX_E_UNSUPPORTED when a request is outside the flat kernel's limits: issue one arx_pool_fwd per lookup then. */
+typedef struct arx_pool_req {
+  const arx_attr_desc* attrs;      /* first descriptor of the attribute range */
+  const int32_t* ent_ids;          /* [n] entity indices */
+  float* out;                      /* [n, out_stride] pooled vectors (mean over attributes) */
+  float* bias_out;                 /* [n] pooled bias or NULL */
+  int64_t n;
+  int64_t out_stride;
+  int32_t n_attr;
+  int32_t max_rows_per_entity;     /* sum over the attributes of the longest bag */
+} arx_pool_req;
+int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream);
+
 /* Integer part of K2 only (mulhot_index.py:48-67): flat token index and segment id
  * vectors for one multi-hot attribute; bit-exact parity target.  offsets[n+1] is an
  * exclusive scan of the bag lengths computed by the caller (device). */
@@ -278,6 +293,18 @@ int arx_lstm_gates_fwd2(float* Z, const float* c_prev, float* c, float* h, float
 int arx_lstm_gates_bwd2(float* G, const float* c_prev, const float* c, const float* dh_out,
                         const float* dh_rec, const float* dc_next, float* dc_prev, int64_t mb, int H,
                         int round_tf32_out, void* stream);
+/* Fused glue of the sampled-WMRB ('mw') step around arx_mw_fwd / arx_mw_bwd (hmf/hmf_model.py:78,112-115;
+ * embed_attribute.py:208-220,236):
+ *   arx_mw_prep: u = u0 / keep * mask (mask NULL: u = u0); U_r = tf32(u); UT [d, M] = U_r^T (NULL: skipped);
+ *                tscore[r] = u[r] . Pt[r] + bt[r] (Pt NULL: skipped); P_r = tf32(Ps) [S, d]; PT [d, S] = P_r^T.
+ *   arx_mw_post: du0 = (dU + dts[r] * Pt) / keep * mask;  dPt = dts[r] * u   (adjoint of the target score + dropout).
+ * inv_keep = 1 / keep_prob.  ARX_E_UNSUPPORTED for shapes outside the vector path (caller uses the separate kernels). */
+int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const float* Pt, const float* bt,
+                const float* Ps, int64_t M, int64_t S, int d, float* u, float* U_r, float* UT, float* tscore,
+                float* P_r, float* PT, void* stream);
+int arx_mw_post(const float* dU, const float* dts, const float* Pt, const float* u, const float* mask,
+                float inv_keep, int64_t M, int d, float* du0, float* dPt, void* stream);
+
 /* K8 as ONE persistent kernel per direction (lstm/seqModel.py:99-103,477: static_rnn over LSTMCell): a cluster of
  * H/32 CTAs owns 128 batch rows for all T steps, W_h resident in shared memory, h W_h on tcgen05 / TMEM, gate
  * non-linearities in the TMEM epilogue, the hidden state all-gathered between the CTAs through distributed shared

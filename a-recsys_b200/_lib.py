@@ -74,8 +74,8 @@ SIGNATURES = {
     'arx_lstm_gates_fwd2': [vp, vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd2': [vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp],
     'arx_pool_fwd_many': [vp, i32, i32, vp],
-    'arx_mw_prep': [vp, vp, f32, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
-    'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp],
+    'arx_mw_prep': [vp, vp, f32, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
+    'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp],
     'arx_lstm_seq_fwd': [vp, vp, vp, vp, i64, i64, i32, f32, vp],
     'arx_lstm_seq_bwd': [vp, vp, vp, vp, i64, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],

@@ -15,11 +15,37 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(r);
 }
 
+// Philox-4x32-10 (Salmon et al., SC'11): counter-based, so the dropout mask needs no generator state on the host and
+// the captured CUDA graph draws a fresh mask on every replay (key = seed, counter = (step, element / 4)).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+// tf.nn.dropout keeps an element when floor(keep + U[0,1)) == 1, i.e. with probability keep
+__device__ __forceinline__ float dropout_keep(const unsigned long long* rng, long long elem, float keep) {
+  const unsigned long long seed = rng[0], step = rng[1];
+  uint32_t o[4];
+  const unsigned long long ctr = (unsigned long long)elem >> 2;
+  philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
+                (uint32_t)(seed >> 32), o);
+  const float u = (float)(o[elem & 3] >> 8) * (1.0f / 16777216.0f);          // [0, 1)
+  return floorf(keep + u);
+}
+
 constexpr int kPrepRows = 32;
 
 // grid: ceil(M / 32) blocks for the batch rows, then ceil(S / 32) blocks for the pool rows; 256 threads
 __global__ void __launch_bounds__(256)
 mw_prep_kernel(const float* __restrict__ u0, const float* __restrict__ mask, float inv_keep,
+               const unsigned long long* __restrict__ rng, float* __restrict__ mask_out,
                const float* __restrict__ Pt, const float* __restrict__ bt, const float* __restrict__ Ps,
                long long M, long long S, int d, float* __restrict__ u, float* __restrict__ U_r,
                float* __restrict__ UT, float* __restrict__ tscore, float* __restrict__ P_r, float* __restrict__ PT) {
@@ -42,6 +68,11 @@ mw_prep_kernel(const float* __restrict__ u0, const float* __restrict__ mask, flo
         x = __ldg(src + row * d + c);
         if (is_u) {
           if (mask != nullptr) x = x * inv_keep * __ldg(mask + row * d + c);      // tf.nn.dropout: x / keep * mask
+          else if (rng != nullptr) {                                              // mask drawn here, kept for the adjoint
+            const float mk = dropout_keep(rng, row * d + c, 1.0f / inv_keep);
+            mask_out[row * d + c] = mk;
+            x = x * inv_keep * mk;
+          }
           u[row * d + c] = x;
           if (Pt != nullptr) dot = fmaf(x, __ldg(Pt + row * d + c), dot);
         }
@@ -65,7 +96,9 @@ mw_prep_kernel(const float* __restrict__ u0, const float* __restrict__ mask, flo
 __global__ void __launch_bounds__(256)
 mw_post_kernel(const float* __restrict__ dU, const float* __restrict__ dts, const float* __restrict__ Pt,
                const float* __restrict__ u, const float* __restrict__ mask, float inv_keep, long long n, int d,
-               float* __restrict__ du0, float* __restrict__ dPt) {
+               float* __restrict__ du0, float* __restrict__ dPt, unsigned long long* __restrict__ rng) {
+  // the step's dropout draw is over (arx_mw_prep ran before this kernel): advance the Philox step counter
+  if (rng != nullptr && blockIdx.x == 0 && threadIdx.x == 0) rng[1] += 1ull;
   const long long stride = (long long)gridDim.x * blockDim.x * 4;
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
     const float g = __ldg(dts + i / d);
@@ -82,22 +115,24 @@ mw_post_kernel(const float* __restrict__ dU, const float* __restrict__ dts, cons
 
 }  // namespace
 
-extern "C" int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const float* Pt, const float* bt,
-                           const float* Ps, int64_t M, int64_t S, int d, float* u, float* U_r, float* UT,
-                           float* tscore, float* P_r, float* PT, void* stream) {
+extern "C" int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const uint64_t* rng_state,
+                           float* mask_out, const float* Pt, const float* bt, const float* Ps, int64_t M, int64_t S,
+                           int d, float* u, float* U_r, float* UT, float* tscore, float* P_r, float* PT, void* stream) {
   if (!u0 || !u || !U_r || M < 0 || S < 0 || d < 1 || (S > 0 && (!Ps || !P_r))) return ARX_E_BADARG;
+  if (!mask && rng_state && !mask_out) return ARX_E_BADARG;
   if (M == 0 && S == 0) return ARX_OK;
   const size_t smem = (size_t)kPrepRows * (d + 1) * sizeof(float);
   if (smem > 48 * 1024) return ARX_E_UNSUPPORTED;
   const long long blocks = (M + kPrepRows - 1) / kPrepRows + (S + kPrepRows - 1) / kPrepRows;
-  mw_prep_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(u0, mask, inv_keep, Pt, bt, Ps, (long long)M,
-                                                                       (long long)S, d, u, U_r, UT, tscore, P_r, PT);
+  mw_prep_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(
+      u0, mask, inv_keep, reinterpret_cast<const unsigned long long*>(rng_state), mask_out, Pt, bt, Ps, (long long)M,
+      (long long)S, d, u, U_r, UT, tscore, P_r, PT);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }
 
 extern "C" int arx_mw_post(const float* dU, const float* dts, const float* Pt, const float* u, const float* mask,
-                           float inv_keep, int64_t M, int d, float* du0, float* dPt, void* stream) {
+                           float inv_keep, int64_t M, int d, float* du0, float* dPt, uint64_t* rng_state, void* stream) {
   if (!dU || !dts || !Pt || !u || !du0 || !dPt || M < 0 || d < 1) return ARX_E_BADARG;
   if (M == 0) return ARX_OK;
   if ((d % 4) || ((uintptr_t)dU & 15) || ((uintptr_t)Pt & 15) || ((uintptr_t)u & 15) || ((uintptr_t)du0 & 15) ||
@@ -106,7 +141,8 @@ extern "C" int arx_mw_post(const float* dU, const float* dts, const float* Pt, c
   const long long n = (long long)M * d;
   const long long b = (n / 4 + 255) / 256;
   const int grid = (int)std::min<long long>(std::max<long long>(b, 1), (long long)arx_num_sms() * 8);
-  mw_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dU, dts, Pt, u, mask, inv_keep, n, d, du0, dPt);
+  mw_post_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dU, dts, Pt, u, mask, inv_keep, n, d, du0, dPt,
+                                                         reinterpret_cast<unsigned long long*>(rng_state));
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

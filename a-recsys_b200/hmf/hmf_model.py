@@ -274,9 +274,6 @@ class LatentProductModel(object):
                 side = m.side_stream(3)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
-                    if keep_prob != 1.0:
-                        dmask = masks[0] if masks else torch.floor(
-                            torch.rand((mb, self.size), dtype=torch.float32, device=self.device) + keep_prob)
                     mwmask = m.mw_mask(mb, S)
                     ev_side = torch.cuda.Event()
                     ev_side.record(side)
@@ -304,9 +301,23 @@ class LatentProductModel(object):
                 P_r = torch.empty((S, d), **f32); PT = torch.empty((d, S), **f32)
                 tscore = torch.empty((mb,), **f32)
                 inv_keep = 1.0 / keep_prob
-                call('arx_mw_prep', u0.data_ptr(), ptr(dmask), inv_keep, Pt.data_ptr(), bt.data_ptr(), Ps.data_ptr(),
-                     mb, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), tscore.data_ptr(), P_r.data_ptr(),
-                     PT.data_ptr())                                            # :78 / embed :236, :115
+                # dropout mask: injected (parity runs) or drawn inside arx_mw_prep (Philox, counter-based: no host
+                # generator state, a fresh mask on every CUDA-graph replay) and kept for the adjoint
+                drng = None
+                if keep_prob != 1.0:
+                    if masks:
+                        dmask = masks[0]
+                    else:
+                        if not hasattr(self, '_drop_rng'):
+                            seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item())     # follows torch.manual_seed
+                            self._drop_rng = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+                        drng = self._drop_rng
+                        dmask_out = torch.empty((mb, d), **f32)
+                call('arx_mw_prep', u0.data_ptr(), ptr(dmask), inv_keep, ptr(drng), dmask_out.data_ptr() if drng is not None else None,
+                     Pt.data_ptr(), bt.data_ptr(), Ps.data_ptr(), mb, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(),
+                     tscore.data_ptr(), P_r.data_ptr(), PT.data_ptr())         # :78 / embed :236, :115
+                if drng is not None:
+                    dmask = dmask_out
                 arena = torch.empty((S + mb, d), **f32)
                 dPt = arena[S:]                   # both item-side gradients land in one arena: no concat
                 fused = m.fused_mw(u, Ps, bs, tscore, scale, True, dP=arena[:S], prepared=(U_r, P_r, UT, PT),
@@ -316,7 +327,7 @@ class LatentProductModel(object):
                 batch_loss, (dU, dPs, dbs, dts) = fused
                 du0 = torch.empty((mb, d), **f32)
                 call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), ptr(dmask), inv_keep,
-                     mb, d, du0.data_ptr(), dPt.data_ptr())
+                     mb, d, du0.data_ptr(), dPt.data_ptr(), ptr(drng))
                 rng = m.sets[pre].attr_range()
                 m.push_grad(pre, rng, sids, POOL_MEAN, dPs, dbs)
                 m.push_grad(pre, rng, item_ids, POOL_MEAN, dPt, dts)

@@ -295,15 +295,20 @@ int arx_lstm_gates_bwd2(float* G, const float* c_prev, const float* c, const flo
                         int round_tf32_out, void* stream);
 /* Fused glue of the sampled-WMRB ('mw') step around arx_mw_fwd / arx_mw_bwd (hmf/hmf_model.py:78,112-115;
  * embed_attribute.py:208-220,236):
- *   arx_mw_prep: u = u0 / keep * mask (mask NULL: u = u0); U_r = tf32(u); UT [d, M] = U_r^T (NULL: skipped);
+ *   arx_mw_prep: u = u0 / keep * mask; U_r = tf32(u); UT [d, M] = U_r^T (NULL: skipped);
  *                tscore[r] = u[r] . Pt[r] + bt[r] (Pt NULL: skipped); P_r = tf32(Ps) [S, d]; PT [d, S] = P_r^T.
- *   arx_mw_post: du0 = (dU + dts[r] * Pt) / keep * mask;  dPt = dts[r] * u   (adjoint of the target score + dropout).
+ *                The dropout mask is either given (`mask`, parity runs), or drawn in the kernel when `rng_state` is
+ *                given (device uint64[2] = {seed, step counter}: Philox-4x32-10, element e uses counter (step, e / 4);
+ *                tf.nn.dropout keeps with probability keep) and written to `mask_out` for the adjoint, or absent
+ *                (both NULL: u = u0).
+ *   arx_mw_post: du0 = (dU + dts[r] * Pt) / keep * mask;  dPt = dts[r] * u   (adjoint of the target score + dropout);
+ *                advances rng_state[1] when given (the step's draw is over).
  * inv_keep = 1 / keep_prob.  ARX_E_UNSUPPORTED for shapes outside the vector path (caller uses the separate kernels). */
-int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const float* Pt, const float* bt,
-                const float* Ps, int64_t M, int64_t S, int d, float* u, float* U_r, float* UT, float* tscore,
-                float* P_r, float* PT, void* stream);
+int arx_mw_prep(const float* u0, const float* mask, float inv_keep, const uint64_t* rng_state, float* mask_out,
+                const float* Pt, const float* bt, const float* Ps, int64_t M, int64_t S, int d, float* u, float* U_r,
+                float* UT, float* tscore, float* P_r, float* PT, void* stream);
 int arx_mw_post(const float* dU, const float* dts, const float* Pt, const float* u, const float* mask,
-                float inv_keep, int64_t M, int d, float* du0, float* dPt, void* stream);
+                float inv_keep, int64_t M, int d, float* du0, float* dPt, uint64_t* rng_state, void* stream);
 
 /* K8 as ONE persistent kernel per direction (lstm/seqModel.py:99-103,477: static_rnn over LSTMCell): a cluster of
  * H/32 CTAs owns 128 batch rows for all T steps, W_h resident in shared memory, h W_h on tcgen05 / TMEM, gate

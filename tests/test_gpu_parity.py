@@ -398,3 +398,51 @@ def test_hmf_ce_fused_tensor_core_path_matches_oracle(cuda, dim, n_items):
     finally:
         _lib.ce_fwd = orig
     assert len(calls) == 5, 'the fused CE path did not run'
+
+
+def test_mw_prep_post_fused_glue_and_philox_dropout(cuda):
+    """arx_mw_prep / arx_mw_post against their unfused definitions; the in-kernel Philox dropout mask is 0/1 with
+    P(keep) = keep_prob, reproducible for a given (seed, step) and different from step to step."""
+    from arecsys_b200._lib import call
+    rng = np.random.default_rng(41)
+    M, S, d, keep = 1000, 260, 128, 0.5
+    f = lambda *sh: torch.tensor(rng.standard_normal(sh).astype(np.float32), device='cuda')
+    u0, Pt, Ps, bt = f(M, d), f(M, d), f(S, d), f(M)
+    mask = torch.tensor(np.floor(rng.random((M, d)) + keep).astype(np.float32), device='cuda')
+    E = lambda *sh: torch.empty(sh, dtype=torch.float32, device='cuda')
+    u, U_r, UT, ts, P_r, PT = E(M, d), E(M, d), E(d, M), E(M), E(S, d), E(d, S)
+    call('arx_mw_prep', u0.data_ptr(), mask.data_ptr(), 1 / keep, None, None, Pt.data_ptr(), bt.data_ptr(), Ps.data_ptr(),
+         M, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), ts.data_ptr(), P_r.data_ptr(), PT.data_ptr())
+    want_u = u0 / keep * mask
+    assert torch.equal(u, want_u)
+    Ur_want = torch.empty_like(u); Pr_want = torch.empty_like(Ps)
+    call('arx_round_tf32', want_u.data_ptr(), Ur_want.data_ptr(), want_u.numel())
+    call('arx_round_tf32', Ps.data_ptr(), Pr_want.data_ptr(), Ps.numel())
+    assert torch.equal(U_r, Ur_want) and torch.equal(P_r, Pr_want)
+    assert torch.equal(UT, Ur_want.t().contiguous()) and torch.equal(PT, Pr_want.t().contiguous())
+    torch.testing.assert_close(ts, (want_u.double() * Pt.double()).sum(1).float() + bt, rtol=1e-5, atol=1e-5)
+    # adjoint glue
+    dU, dts = f(M, d), f(M)
+    du0, dPt = E(M, d), E(M, d)
+    call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), mask.data_ptr(), 1 / keep, M, d,
+         du0.data_ptr(), dPt.data_ptr(), None)
+    torch.testing.assert_close(du0, (dU + dts[:, None] * Pt) / keep * mask, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(dPt, dts[:, None] * u, rtol=1e-6, atol=1e-6)
+    # in-kernel dropout draw
+    state = torch.tensor([1234, 0], dtype=torch.int64, device='cuda')
+    m1, m2, m3 = E(M, d), E(M, d), E(M, d)
+    for mo in (m1, m2):
+        call('arx_mw_prep', u0.data_ptr(), None, 1 / keep, state.data_ptr(), mo.data_ptr(), Pt.data_ptr(), bt.data_ptr(),
+             Ps.data_ptr(), M, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), ts.data_ptr(), P_r.data_ptr(), PT.data_ptr())
+    assert torch.equal(m1, m2) and torch.equal(u, u0 / keep * m1)                 # same (seed, step): same mask
+    assert set(torch.unique(m1).tolist()) <= {0.0, 1.0}
+    n = M * d
+    assert abs(float(m1.mean()) - keep) < 5 * (keep * (1 - keep) / n) ** 0.5
+    assert abs(float(m1.mean(0).std()) - (keep * (1 - keep) / M) ** 0.5) < 0.3 * (keep * (1 - keep) / M) ** 0.5   # no column structure
+    call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), m1.data_ptr(), 1 / keep, M, d,
+         du0.data_ptr(), dPt.data_ptr(), state.data_ptr())
+    assert state.tolist() == [1234, 1]                                              # the step counter advanced
+    call('arx_mw_prep', u0.data_ptr(), None, 1 / keep, state.data_ptr(), m3.data_ptr(), Pt.data_ptr(), bt.data_ptr(),
+         Ps.data_ptr(), M, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), ts.data_ptr(), P_r.data_ptr(), PT.data_ptr())
+    agree = float((m1 == m3).float().mean())
+    assert 0.45 < agree < 0.55                                                      # independent of the previous step's mask

@@ -38,6 +38,12 @@ class BwdPlan(ctypes.Structure):
                 ('cap_rows', ctypes.c_int64), ('cap_occ', ctypes.c_int64), ('cap_chunks', ctypes.c_int64)]
 
 
+class ApplySet(ctypes.Structure):
+    """arx_apply_set (include/arx_b200.h)."""
+    _fields_ = [('attrs', vp), ('dout', vp), ('dbias', vp), ('dout_stride', ctypes.c_int64), ('plan', BwdPlan),
+                ('n_attr', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
 POOL_MEAN, POOL_CONCAT = 0, 1
 OPT_ADAGRAD, OPT_SGD, OPT_NONE = 0, 1, 2
 LOSS_KIND = {'ce': 0, 'warp': 1, 'warp_eval': 1, 'rs': 2, 'rs-sig': 3, 'rs-sig2': 4, 'bbpr': 5, 'mw': 6}
@@ -56,6 +62,7 @@ SIGNATURES = {
     'arx_bwd_plan_end': [vp, BwdPlan, vp],
     'arx_pool_bwd_plan': [vp, i32, vp, i64, i32, BwdPlan, vp],
     'arx_pool_bwd_apply': [vp, i32, i32, BwdPlan, vp, i64, vp, f32, vp, i32, vp, vp, vp],
+    'arx_pool_bwd_apply_many': [vp, i32, i32, f32, vp, i32, vp],
     'arx_pool_bwd_sumsq': [vp, i32, BwdPlan, vp, i64, vp, vp, i32, vp],
     'arx_rows_sumsq': [vp, vp, BwdPlan, i32, vp, vp],
     'arx_set_tuning': [ctypes.c_char_p, i32],
@@ -69,6 +76,7 @@ SIGNATURES = {
     'arx_mw_mask_build': [vp, vp, vp, i64, i64, vp, i64, vp],
     'arx_mw_fwd': [vp, vp, vp, vp, vp, i64, i64, i64, i64, vp, vp, vp, vp],
     'arx_mw_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp],
+    'arx_mw_bwd2': [vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, i64, i64, vp, vp, vp, vp, i32, vp],
     'arx_lstm_gates_fwd': [vp, vp, vp, vp, i64, i32, f32, vp],
     'arx_lstm_gates_bwd': [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     'arx_lstm_gates_fwd2': [vp, vp, vp, vp, vp, i64, i32, f32, vp],
@@ -156,8 +164,8 @@ def call(name, *args):
     return rc
 
 
-_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd', 'arx_lstm_seq_fwd',
-                       'arx_lstm_seq_bwd', 'arx_pool_fwd_many', 'arx_mw_prep', 'arx_mw_post')
+_MAY_BE_UNSUPPORTED = ('arx_gemm_tc', 'arx_ce_fwd', 'arx_ce_bwd', 'arx_mw_fwd', 'arx_mw_bwd', 'arx_mw_bwd2', 'arx_lstm_seq_fwd',
+                       'arx_lstm_seq_bwd', 'arx_pool_fwd_many', 'arx_mw_prep', 'arx_mw_post', 'arx_pool_bwd_apply_many')
 exact_fp32 = False   # True: every contraction on the exact-fp32 SIMT kernel (parity anchor runs)
 
 
@@ -268,7 +276,7 @@ def mw_fwd(U_r, P_r, beta, tscore, mask, mask_ld, M, N, d):
     return hsum, loss
 
 
-def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=None, PT=None):
+def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=None, PT=None, outputs=None):
     """(dU, dP, dbeta, dts) of sum_r g[r] * loss[r].  UT / PT: the transposed operands when the caller already has
     them (arx_mw_prep emits them with the rounding pass)."""
     dev = U_r.device
@@ -278,13 +286,18 @@ def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=
     if PT is None:
         PT = torch.empty((d, N), dtype=torch.float32, device=dev)
         call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
-    dU = torch.empty((M, d), dtype=torch.float32, device=dev)
-    if dP is None:
-        dP = torch.empty((N, d), dtype=torch.float32, device=dev)
-    dbeta = torch.empty((N,), dtype=torch.float32, device=dev)
-    dts = torch.empty((M,), dtype=torch.float32, device=dev)
-    if call('arx_mw_bwd', U_r.data_ptr(), P_r.data_ptr(), UT.data_ptr(), PT.data_ptr(), ptr(beta), tscore.data_ptr(),
+    zeroed = 0
+    if outputs is not None:                     # (dU, dP, dbeta, dts) zeroed by the caller, off the dependent chain
+        dU, dP, dbeta, dts = outputs
+        zeroed = 1
+    else:
+        dU = torch.empty((M, d), dtype=torch.float32, device=dev)
+        if dP is None:
+            dP = torch.empty((N, d), dtype=torch.float32, device=dev)
+        dbeta = torch.empty((N,), dtype=torch.float32, device=dev)
+        dts = torch.empty((M,), dtype=torch.float32, device=dev)
+    if call('arx_mw_bwd2', U_r.data_ptr(), P_r.data_ptr(), UT.data_ptr(), PT.data_ptr(), ptr(beta), tscore.data_ptr(),
             ptr(mask), mask_ld, hsum.data_ptr(), g.data_ptr(), M, N, d, dU.data_ptr(), dP.data_ptr(), dbeta.data_ptr(),
-            dts.data_ptr()) != 0:
+            dts.data_ptr(), zeroed) != 0:
         return None
     return dU, dP, dbeta, dts

@@ -447,7 +447,7 @@ class EmbeddingAttribute(object):
         return mask, ld
 
     def fused_mw(self, latent, Ps, bs, tscore, row_scale, want_grad, forward_only=False, pos_rows=None, dP=None,
-                 prepared=None, mask=None):
+                 prepared=None, mask=None, outputs=None):
         """Sampled-pool scoring (:148-206, pool='sampled') + _compute_mw_loss (:641-649) + their gradients on the
         tensor cores without writing the [rows, S] scores: arx_mw_mask_build / arx_mw_fwd / arx_mw_bwd.
         Returns (loss_rows, (dU, dPs, dbs, dts) or None), or None when the shape is not supported."""
@@ -471,7 +471,7 @@ class EmbeddingAttribute(object):
         if not want_grad:
             return loss, None
         g = row_scale if row_scale is not None else torch.ones(M, dtype=torch.float32, device=self.device)
-        grads = _lib.mw_bwd(U_r, P_r, bs, tscore, mask, ld, hsum, g, M, S, d, dP=dP, UT=UT, PT=PT)
+        grads = _lib.mw_bwd(U_r, P_r, bs, tscore, mask, ld, hsum, g, M, S, d, dP=dP, UT=UT, PT=PT, outputs=outputs)
         if grads is None:
             return None
         return loss, grads
@@ -799,6 +799,36 @@ class EmbeddingAttribute(object):
         # captured CUDA graph) so that their memory traffic overlaps.
         main = torch.cuda.current_stream()
         busy = [ts for ts in self.sets.values() if ts.pending]
+        if (busy and self.dim <= 128 and self.dim % 4 == 0 and opt in (OPT_ADAGRAD, OPT_SGD)
+                and os.environ.get('ARX_APPLY_MANY', '1') == '1'):
+            # every table set of the step in one launch (two per call): arx_pool_bwd_apply_many
+            ready_all = []
+            for ts in busy:
+                ready = getattr(ts, '_ready', None)
+                if ready is not None:
+                    ts._ready = None
+                else:
+                    ready = (self._plan_for(ts, ts.pending), ) + self._arena(ts.pending)
+                ready_all.append(ready)
+            ok = True
+            for k0 in range(0, len(busy), 2):
+                grp = list(zip(busy[k0:k0 + 2], ready_all[k0:k0 + 2]))
+                sets = (_lib.ApplySet * len(grp))()
+                for q, (ts, (plan, arena, bias)) in zip(sets, grp):
+                    q.attrs, q.dout, q.dbias = ts.desc_ptr(0), arena.data_ptr(), ptr(bias)
+                    q.dout_stride, q.plan, q.n_attr = arena.stride(0), plan.c, ts.n_attr
+                _lib.tag = '+'.join(ts.prefix for ts, _ in grp)
+                if call('arx_pool_bwd_apply_many', ctypes.addressof(sets), len(grp), self.dim, float(lr), ptr(grad_scale),
+                        opt) != 0:
+                    ok = False
+                    break
+            if ok:
+                for ts in busy:
+                    ts.pending = []
+                self._after_apply()
+                return
+            for ts, ready in zip(busy, ready_all):           # not supported: per-set launches below
+                ts._ready = ready
         forks = []
         for k, ts in enumerate(busy):
             side = self.side_stream(k) if (len(busy) > 1 and k > 0 and _lib.timeline is None) else None
@@ -819,6 +849,9 @@ class EmbeddingAttribute(object):
             ts.pending = []
         for side in forks:
             main.wait_stream(side)
+        self._after_apply()
+
+    def _after_apply(self):
         # A plan that ran out of capacity makes plan_fill / apply return without touching anything: surface it instead
         # of training on silently.  Reading the flag synchronises, so: every 256th eager call, never during capture.
         self._apply_calls = getattr(self, '_apply_calls', 0) + 1

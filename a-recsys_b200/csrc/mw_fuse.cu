@@ -9,10 +9,12 @@
 
 namespace {
 
+// same rounding as arx_round_tf32 (optim.cu): nearest tf32, ties to even — the fused and the unfused glue agree bit for bit
 __device__ __forceinline__ float tf32_round(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+  unsigned int u = __float_as_uint(x);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0x00000fffu + ((u >> 13) & 1u);
+  return __uint_as_float(u & 0xffffe000u);
 }
 
 // Philox-4x32-10 (Salmon et al., SC'11): counter-based, so the dropout mask needs no generator state on the host and

@@ -614,9 +614,22 @@ extern "C" int arx_mw_fwd(const float* U, const float* P, const float* beta, con
   return ARX_OK;
 }
 
+extern "C" int arx_mw_bwd2(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
+                           const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
+                           int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts,
+                           int outputs_zeroed, void* stream);
 extern "C" int arx_mw_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                           const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
                           int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, void* stream) {
+  return arx_mw_bwd2(U, P, UT, PT, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dU, dP, dbeta, dts, 0, stream);
+}
+
+// outputs_zeroed != 0: the caller has already zeroed dU, dP, dbeta and dts (e.g. with one memset at the top of the step,
+// off the dependent chain): the split accumulation then starts without the four memsets in front of the kernels.
+extern "C" int arx_mw_bwd2(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
+                           const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
+                           int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts,
+                           int outputs_zeroed, void* stream) {
   if (!U || !P || !UT || !PT || !tscore || !hsum || !g || !dU || !dP || !dts) return ARX_E_BADARG;
   if (!ce_shape_ok(M, N, d) || (M % 4) || (N % 4) || ((uintptr_t)U & 15) || ((uintptr_t)P & 15) ||
       ((uintptr_t)UT & 15) || ((uintptr_t)PT & 15) || (mask && (mask_ld % 4)))
@@ -634,7 +647,7 @@ extern "C" int arx_mw_bwd(const float* U, const float* P, const float* UT, const
     CeParams p{};
     p.R = M; p.S = N; p.d = (int)d; p.tiles_per_split = tps; p.beta = beta; p.lse = hsum; p.g = g; p.ts = tscore;
     p.mask = mask; p.mask_ld = mask_ld; p.out = dU; p.dts = dts; p.atomic_out = nsplit > 1;
-    if (p.atomic_out) {
+    if (p.atomic_out && !outputs_zeroed) {
       if (cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)M * d, st) != cudaSuccess) return ARX_E_LAUNCH;
       if (cudaMemsetAsync(dts, 0, sizeof(float) * (size_t)M, st) != cudaSuccess) return ARX_E_LAUNCH;
     }
@@ -648,7 +661,7 @@ extern "C" int arx_mw_bwd(const float* U, const float* P, const float* UT, const
     CeParams p{};
     p.R = N; p.S = M; p.d = (int)d; p.tiles_per_split = tps; p.beta = beta; p.lse = hsum; p.g = g; p.ts = tscore;
     p.mask = mask; p.mask_ld = mask_ld; p.out = dP; p.dbeta = dbeta; p.atomic_out = nsplit > 1;
-    if (p.atomic_out) {
+    if (p.atomic_out && !outputs_zeroed) {
       if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)N * d, st) != cudaSuccess) return ARX_E_LAUNCH;
       if (dbeta && cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)N, st) != cudaSuccess) return ARX_E_LAUNCH;
     }

@@ -274,6 +274,11 @@ class LatentProductModel(object):
                 side = m.side_stream(3)
                 side.wait_stream(main)
                 with torch.cuda.stream(side):
+                    # one memset for every buffer the split accumulation of arx_mw_bwd adds into:
+                    # the gradient arena (pool rows | target rows), dU and the bias-gradient arena
+                    arena = torch.zeros((S + mb, self.size), dtype=torch.float32, device=self.device)
+                    dU_z = torch.zeros((mb, self.size), dtype=torch.float32, device=self.device)
+                    zb = torch.zeros((S + mb,), dtype=torch.float32, device=self.device)      # bias gradients: pool | targets
                     mwmask = m.mw_mask(mb, S)
                     ev_side = torch.cuda.Event()
                     ev_side.record(side)
@@ -318,10 +323,10 @@ class LatentProductModel(object):
                      tscore.data_ptr(), P_r.data_ptr(), PT.data_ptr())         # :78 / embed :236, :115
                 if drng is not None:
                     dmask = dmask_out
-                arena = torch.empty((S + mb, d), **f32)
                 dPt = arena[S:]                   # both item-side gradients land in one arena: no concat
+                outs = (dU_z, arena[:S], zb[:S], zb[S:])
                 fused = m.fused_mw(u, Ps, bs, tscore, scale, True, dP=arena[:S], prepared=(U_r, P_r, UT, PT),
-                                   mask=mwmask)
+                                   mask=mwmask, outputs=outs)
                 if fused is None:
                     raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
                 batch_loss, (dU, dPs, dbs, dts) = fused

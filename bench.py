@@ -390,7 +390,7 @@ def main():
     # ---------------- per-kernel durations and roofline -----------------------------------
     agg = {}
     for name, tag, s0, s1 in tl:
-        k = '%s:%s' % (name, tag) if name in ('arx_pool_fwd', 'arx_pool_bwd_apply', 'arx_pool_fwd_many') else name
+        k = '%s:%s' % (name, tag) if name in ('arx_pool_fwd', 'arx_pool_bwd_apply', 'arx_pool_fwd_many', 'arx_pool_bwd_apply_many') else name
         d = agg.setdefault(k, [0.0, 0])
         d[0] += s0.elapsed_time(s1)
         d[1] += 1
@@ -425,6 +425,9 @@ def main():
                  'pool_fwd_flat_many_kernel<1>: users + sampled pool + target items, %d entities' % (2 * a.mb + len(pool_ids)))
             roof('arx_pool_bwd_apply:item', ib2['bwd_unique'], ib2['bwd_nominal'],
                  'pool_bwd_apply_kernel<4> item side (pool + targets, %d entity rows)' % (len(pool_ids) + len(item_ids)))
+            # both applies as ONE launch (arx_pool_bwd_apply_many): user set + item set
+            roof('arx_pool_bwd_apply_many:user+item', ub['bwd_unique'] + ib2['bwd_unique'], ub['bwd_nominal'] + ib2['bwd_nominal'],
+                 'pool_bwd_apply2_kernel: user tables + item tables (pool + targets) in one launch')
             # whole step against the HBM roofline: embedding forward + backward bytes of both sides,
             # unique-row accounting, over the measured step time (everything else in the step counts as overhead)
             step_bytes = ub['fwd_unique'] + ub['bwd_unique'] + ib2['fwd_unique'] + ib2['bwd_unique']

@@ -150,6 +150,21 @@ int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int dim,
                        const float* dbias, float lr, const float* grad_scale_dev,
                        int opt, float* rows_out, float* bias_rows_out, void* stream);
 
+/* The same optimizer step for up to two table sets in ONE launch (the user and the item tables of a training step:
+ * hmf/hmf_model.py:146-151 applies every gradient in one session.run).  ARX_OPT_ADAGRAD / ARX_OPT_SGD, dim <= 128,
+ * dim % 4 == 0; ARX_E_UNSUPPORTED otherwise. */
+typedef struct arx_apply_set {
+  const arx_attr_desc* attrs;      /* all descriptors of the table set */
+  const float* dout;               /* gradient arena [R, dout_stride] */
+  const float* dbias;              /* [R] bias-gradient arena or NULL */
+  int64_t dout_stride;
+  arx_bwd_plan plan;
+  int32_t n_attr;
+  int32_t reserved;
+} arx_apply_set;
+int arx_pool_bwd_apply_many(const arx_apply_set* sets, int n_sets, int dim, float lr, const float* grad_scale_dev,
+                            int opt, void* stream);
+
 /* Squared-norm term of tf.clip_by_global_norm (lstm/seqModel.py:180), accumulated into *sumsq
  * (device).  merged = 0: IndexedSlices semantics, sum over OCCURRENCES of ||w * dOut[row]||^2
  * (tables reached only through lookups; TF does not merge duplicate slices for the norm).
@@ -264,6 +279,11 @@ int arx_mw_fwd(const float* U, const float* P, const float* beta, const float* t
 int arx_mw_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
                int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, void* stream);
+/* Same, with outputs_zeroed != 0 when the caller has zeroed dU, dP, dbeta and dts itself (off the dependent chain). */
+int arx_mw_bwd2(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
+                const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
+                int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, int outputs_zeroed,
+                void* stream);
 
 /* K4 — target_score[b] = U[b].P[b] + beta[b] (embed_attribute.py:219-220) and its adjoint
  * dU[b] += dts[b] P[b]; dP[b] = dts[b] U[b]. */

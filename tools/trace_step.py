@@ -64,6 +64,16 @@ def main():
         print('%8.1f %7.1f %8.1f  s%-3s %s' % (st, e.time_range.elapsed_us(), st + e.time_range.elapsed_us(),
                                               getattr(e, 'device_index', '?') if False else '', e.name[:90]))
     print('# step span: %.1f us' % (last[-1].time_range.end - t0))
+    # device idle time between consecutive replays (end of the last kernel of a step -> first id copy of the next)
+    pairs = [starts[i] for i in range(0, len(starts) - 1, 2)]
+    for a_, b_ in zip(pairs[:-1], pairs[1:]):
+        seg = evs[a_:b_]
+        end = max(e.time_range.end for e in seg)
+        print('# replay: span %.1f us, idle before the next replay %.1f us' % (
+            end - seg[0].time_range.start, evs[b_].time_range.start - end))
+    cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU and 'cudaGraphLaunch' in e.name]
+    if cpu:
+        print('# cudaGraphLaunch host time: %s us' % [round(e.time_range.elapsed_us(), 1) for e in cpu])
 
 
 if __name__ == '__main__':

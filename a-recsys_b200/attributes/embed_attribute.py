@@ -799,9 +799,11 @@ class EmbeddingAttribute(object):
         # captured CUDA graph) so that their memory traffic overlaps.
         main = torch.cuda.current_stream()
         busy = [ts for ts in self.sets.values() if ts.pending]
-        if (busy and self.dim <= 128 and self.dim % 4 == 0 and opt in (OPT_ADAGRAD, OPT_SGD)
-                and os.environ.get('ARX_APPLY_MANY', '1') == '1'):
-            # every table set of the step in one launch (two per call): arx_pool_bwd_apply_many
+        if (busy and self.dim % 4 == 0 and opt in (OPT_ADAGRAD, OPT_SGD)
+                and os.environ.get('ARX_APPLY_MANY', '0') == '1'):
+            # every table set of the step in one launch (two per call): arx_pool_bwd_apply_many.  OFF by default:
+            # measured at C2 the merged launch is slower than two launches on parallel streams (334-384 us vs
+            # 117 + 138 us; the doubled body costs registers and spills) — kept as an A/B switch only.
             ready_all = []
             for ts in busy:
                 ready = getattr(ts, '_ready', None)

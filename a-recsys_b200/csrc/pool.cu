@@ -804,15 +804,13 @@ __device__ __forceinline__ void row_update(const arx_attr_desc& a, size_t off, t
 constexpr int kRowsPerStep = 4;
 
 template <int VEC>
-__global__ void __launch_bounds__(256, 2)
-pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
-                       arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
-                       const float* __restrict__ dbias, float lr,
-                       const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
-                       float* __restrict__ bias_rows_out) {
+__device__ __forceinline__ void
+pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
+                    const arx_bwd_plan& plan, const float* __restrict__ dout, long long dout_stride,
+                    const float* __restrict__ dbias, float lr,
+                    const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
+                    float* __restrict__ bias_rows_out) {
   using VT = typename V<VEC>::T;
-  __shared__ arx_attr_desc s_attrs[kMaxAttr];
-  stage_descs(s_attrs, g_attrs, n_attr);
   if (plan.counters[2] != 0) return;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -964,17 +962,20 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
   }
 }
 
-// ---- apply, second generation: dim <= 128 (one float4 column per lane), several table sets per launch -----------
-// What the timeline and ncu showed for pool_bwd_apply_kernel at C2: 2 CTAs/SM of 128 registers, and per group of four rows
-// the loads came in dependent waves — table + accumulator rows and the first gradient row, then, for every row with more
-// than one contribution (the item side: 2.7 on average), one further dependent wave per row.  Bytes in flight per SM stayed
-// near the latency-bandwidth product only part of the time (4.0 of 6.5 TB/s).  Here, per group of four rows:
-//   * the table and accumulator rows are requested first (HBM);
-//   * the bucket entries of all four rows are fetched as ONE flat, coalesced list (rows that a warp takes have adjacent
-//     buckets: plan_alloc numbers them with a warp scan) and their gradient rows (L2-resident arena) are gathered eight at
-//     a time ACROSS row boundaries, each landing in its row's accumulator through predicated FMAs;
-//   * both table sets of a step run in one launch (a warp that runs out of rows of the first set continues with the second:
-//     one ramp, one tail).
+template <int VEC>
+__global__ void __launch_bounds__(256, 2)
+pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
+                       arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
+                       const float* __restrict__ dbias, float lr,
+                       const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
+                       float* __restrict__ bias_rows_out) {
+  __shared__ arx_attr_desc s_attrs[kMaxAttr];
+  stage_descs(s_attrs, g_attrs, n_attr);
+  pool_bwd_apply_body<VEC>(s_attrs, dim, plan, dout, dout_stride, dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+}
+
+// Several table sets (the user and the item tables of one training step) in ONE launch: a warp that has run out of rows
+// of the first set goes straight on to the second — one launch ramp and one tail instead of two.
 struct ApplySet {
   const arx_attr_desc* attrs;
   const float* dout;
@@ -992,192 +993,24 @@ struct ApplyManyParams {
 };
 
 __global__ void __launch_bounds__(256, 2)
-pool_bwd_apply2_kernel(const ApplyManyParams mp) {
-  using VT = float4;
+pool_bwd_apply_many_kernel(const ApplyManyParams mp) {
   __shared__ arx_attr_desc s_attrs_all[kApplySets][kMaxAttr];
-  for (int si = 0; si < mp.n_sets; ++si) {
+#pragma unroll
+  for (int si = 0; si < kApplySets; ++si) {
+    if (si >= mp.n_sets) break;
     const int words = mp.set[si].n_attr * (int)(sizeof(arx_attr_desc) / 8);
     const unsigned long long* src = reinterpret_cast<const unsigned long long*>(mp.set[si].attrs);
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(s_attrs_all[si]);
     for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const int dim = mp.dim, opt = mp.opt;
-  const int nvec = dim >> 2;
-  const bool colok = lane < nvec;
-  const int col = lane;
-  const float lr = mp.lr;
-  const float gs = mp.grad_scale ? __ldg(mp.grad_scale) : 1.0f;
-
-  // ---- phase 1 (every set): chunks of the hot rows, longest work first --------------------------------------------
-  for (int si = 0; si < mp.n_sets; ++si) {
-    const ApplySet& S = mp.set[si];
-    const arx_bwd_plan& plan = S.plan;
-    if (plan.counters[2] != 0) continue;
-    const arx_attr_desc* s_attrs = s_attrs_all[si];
-    const int nchunks = (int)min((long long)plan.counters[4], (long long)plan.cap_chunks);
-    float* __restrict__ part = plan.partials;
-    float* __restrict__ part_b = plan.partials + (size_t)plan.cap_chunks * dim;
-    for (long long ch = warp0; ch < nchunks; ch += nwarps) {
-      const int u = plan.chunk_row[ch];
-      const int cb = plan.row_chunk0[u];
-      const int k = (int)ch - cb;
-      const int rc = plan.row_cnt[u];
-      const int base = plan.row_base[u] + k * kHeavy;
-      const int cnt = min(kHeavy, rc - k * kHeavy);
-      const int nch = (rc + kHeavy - 1) / kHeavy;
-      {
-        float gb_unused;
-        const VT g = reduce_bucket<4>(plan, base, cnt, S.dout, S.dout_stride, col, colok, lane, nullptr, gb_unused);
-        if (colok) st_f4(part + (size_t)ch * dim + (size_t)col * 4, g);
-      }
-      if (S.dbias != nullptr) {
-        float gb = 0.f;
-        for (int kk = lane; kk < cnt; kk += 32)
-          gb = fmaf(__ldg(plan.bucket_w + base + kk), __ldg(S.dbias + __ldg(plan.bucket_src + base + kk)), gb);
-        gb = warp_sum(gb);
-        if (lane == 0) part_b[ch] = gb;
-      }
-      __threadfence();
-      int last = 0;
-      if (lane == 0) last = (atomicAdd(&plan.row_done[u], 1) == nch - 1) ? 1 : 0;
-      last = __shfl_sync(ARX_FULL_MASK, last, 0);
-      if (!last) continue;
-      __threadfence();
-      const int f = plan.uniq_attr[u];
-      const int tok = local_row(shard_of(s_attrs[f]), plan.uniq_tok[u]);
-      if (colok) {
-        VT g = f4_zero();
-        for (int kk0 = 0; kk0 < nch; kk0 += kRowsInFlight) {      // fixed chunk order
-          VT v[kRowsInFlight];
-#pragma unroll
-          for (int q = 0; q < kRowsInFlight; ++q)
-            v[q] = (kk0 + q < nch) ? __ldcg(reinterpret_cast<const float4*>(part + (size_t)(cb + kk0 + q) * dim + (size_t)col * 4))
-                                   : f4_zero();
-#pragma unroll
-          for (int q = 0; q < kRowsInFlight; ++q) f4_add(g, v[q]);
-        }
-        g = f4_scale(g, gs);
-        row_update<4>(s_attrs[f], (size_t)tok * dim + (size_t)col * 4, g, lr, opt);
-      }
-      if (lane == 0) {
-        if (S.dbias != nullptr && s_attrs[f].bias != nullptr) {
-          float gb = 0.f;
-          for (int kk = 0; kk < nch; ++kk) gb += __ldcg(part_b + cb + kk);
-          bias_update(s_attrs[f], tok, gb * gs, lr, opt);
-        }
-        plan.row_done[u] = 0;
-      }
-    }
-  }
-
-  // ---- phase 2 (every set): all other rows, 32 per warp iteration, four per step -------------------------------------
-  for (int si = 0; si < mp.n_sets; ++si) {
-    const ApplySet& S = mp.set[si];
-    const arx_bwd_plan& plan = S.plan;
-    if (plan.counters[2] != 0) continue;
-    const arx_attr_desc* s_attrs = s_attrs_all[si];
-    const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
-    const float* __restrict__ dout = S.dout;
-    const long long dstride = S.dout_stride;
-    const float* __restrict__ dbias = S.dbias;
-    for (long long u0 = warp0 * 32; u0 < nu; u0 += nwarps * 32) {
-      const int u = (int)u0 + lane;
-      int tok = 0, f = 0, base = 0, cnt = 0;
-      if (u < nu) {
-        f = __ldg(plan.uniq_attr + u);
-        tok = local_row(shard_of(s_attrs[f]), __ldg(plan.uniq_tok + u));
-        base = __ldg(plan.row_base + u); cnt = __ldg(plan.row_cnt + u);
-      }
-      const int lcnt = (u < nu && cnt <= kHeavy) ? cnt : 0;      // 0: nothing to do here (absent or hot row)
-      const bool has_bias = dbias != nullptr && lcnt > 0 && s_attrs[f].bias != nullptr;
-      float gb_mine = 0.f;
-#pragma unroll 1
-      for (int r = 0; r < 32; r += kRowsPerStep) {
-        int cq[kRowsPerStep], bq[kRowsPerStep], tq[kRowsPerStep], fq[kRowsPerStep];
-        int tot = 0;
-#pragma unroll
-        for (int q = 0; q < kRowsPerStep; ++q) {
-          cq[q] = __shfl_sync(ARX_FULL_MASK, lcnt, r + q);
-          bq[q] = __shfl_sync(ARX_FULL_MASK, base, r + q);
-          tq[q] = __shfl_sync(ARX_FULL_MASK, tok, r + q);
-          fq[q] = __shfl_sync(ARX_FULL_MASK, f, r + q);
-          tot += cq[q];
-        }
-        if (tot == 0) continue;
-        // (1) table + accumulator rows: the long-latency requests go out first
-        VT Ev[kRowsPerStep], Av[kRowsPerStep], g[kRowsPerStep];
-#pragma unroll
-        for (int q = 0; q < kRowsPerStep; ++q) {
-          Ev[q] = f4_zero(); Av[q] = f4_zero(); g[q] = f4_zero();
-          if (cq[q] > 0 && colok) {
-            const size_t off = (size_t)tq[q] * dim + (size_t)col * 4;
-            Ev[q] = ld_f4(s_attrs[fq[q]].table + off);
-            if (opt == ARX_OPT_ADAGRAD) Av[q] = ld_f4(s_attrs[fq[q]].table_acc + off);
-          }
-        }
-        // (2) the four buckets as one flat list of (gradient row, weight, row slot) entries
-        const int e1 = cq[0], e2 = e1 + cq[1], e3 = e2 + cq[2];
-        float gbq[kRowsPerStep] = {0.f, 0.f, 0.f, 0.f};
-        for (int j0 = 0; j0 < tot; j0 += 32) {
-          const int j = j0 + lane;
-          int src = 0, slot = 0; float w = 0.f;
-          if (j < tot) {
-            slot = (j >= e1) + (j >= e2) + (j >= e3);
-            const int pre = slot == 0 ? 0 : (slot == 1 ? e1 : (slot == 2 ? e2 : e3));
-            const int bb = slot == 0 ? bq[0] : (slot == 1 ? bq[1] : (slot == 2 ? bq[2] : bq[3]));
-            src = __ldg(plan.bucket_src + bb + (j - pre));
-            w = __ldg(plan.bucket_w + bb + (j - pre));
-          }
-          if (dbias != nullptr) {                         // bias column: one entry per lane, four segmented sums
-            const float bw = (j < tot) ? w * __ldg(dbias + src) : 0.f;
-#pragma unroll
-            for (int q = 0; q < kRowsPerStep; ++q) gbq[q] += warp_sum(slot == q ? bw : 0.f);
-          }
-          const int kc = min(32, tot - j0);
-          constexpr int kGather = 4;                     // gradient rows in flight (the arena is L2-resident)
-          for (int kk0 = 0; kk0 < kc; kk0 += kGather) {
-            VT v[kGather]; float wk[kGather]; int sq[kGather];
-#pragma unroll
-            for (int i = 0; i < kGather; ++i) {
-              const int kk = kk0 + i;
-              const int sk = __shfl_sync(ARX_FULL_MASK, src, kk & 31);
-              wk[i] = (kk < kc) ? __shfl_sync(ARX_FULL_MASK, w, kk & 31) : 0.f;
-              sq[i] = __shfl_sync(ARX_FULL_MASK, slot, kk & 31);
-              v[i] = (kk < kc && colok) ? ldg_f4(dout + (size_t)sk * dstride + (size_t)col * 4) : f4_zero();
-            }
-#pragma unroll
-            for (int i = 0; i < kGather; ++i) {
-#pragma unroll
-              for (int q = 0; q < kRowsPerStep; ++q) f4_fma(g[q], sq[i] == q ? wk[i] : 0.f, v[i]);
-            }
-          }
-        }
-        // (3) optimizer update of the four rows
-#pragma unroll
-        for (int q = 0; q < kRowsPerStep; ++q) {
-          if (cq[q] == 0) continue;
-          if (colok) {
-            const VT gq = f4_scale(g[q], gs);
-            const size_t off = (size_t)tq[q] * dim + (size_t)col * 4;
-            if (opt == ARX_OPT_ADAGRAD) {
-              V<4>::adagrad(Ev[q], Av[q], gq, lr);
-              st_f4(s_attrs[fq[q]].table_acc + off, Av[q]);
-              st_f4(s_attrs[fq[q]].table + off, Ev[q]);
-            } else {
-              V<4>::sgd(Ev[q], gq, lr);
-              st_f4(s_attrs[fq[q]].table + off, Ev[q]);
-            }
-          }
-          if (lane == r + q) gb_mine = gbq[q];
-        }
-      }
-      if (has_bias) bias_update(s_attrs[f], tok, gb_mine * gs, lr, opt);
-    }
-  }
+  // constant indices into the parameter block: a run-time index would make the compiler copy the parameters to local
+  // memory and read every plan pointer through it inside the inner loops
+  pool_bwd_apply_body<4>(s_attrs_all[0], mp.dim, mp.set[0].plan, mp.set[0].dout, mp.set[0].dout_stride, mp.set[0].dbias,
+                         mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr);
+  if (mp.n_sets > 1)
+    pool_bwd_apply_body<4>(s_attrs_all[1], mp.dim, mp.set[1].plan, mp.set[1].dout, mp.set[1].dout_stride, mp.set[1].dbias,
+                           mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr);
 }
 
 // IndexedSlices part of the global norm: sum over occurrences of w^2 * ||dOut[src]||^2
@@ -1478,13 +1311,12 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
 }
 
 // De-duplicated optimizer step of up to two table sets (e.g. the user and the item tables of one training step) in one
-// launch; dim <= 128 with dim % 4 == 0, ARX_OPT_ADAGRAD / ARX_OPT_SGD.  ARX_E_UNSUPPORTED otherwise (one
-// arx_pool_bwd_apply per set then).
+// launch; dim % 4 == 0, ARX_OPT_ADAGRAD / ARX_OPT_SGD.  ARX_E_UNSUPPORTED otherwise (one arx_pool_bwd_apply per set then).
 extern "C" int arx_pool_bwd_apply_many(const arx_apply_set* sets, int n_sets, int dim, float lr,
                                        const float* grad_scale_dev, int opt, void* stream) {
   if (!sets || n_sets < 1 || n_sets > kApplySets || dim < 1) return ARX_E_BADARG;
   if (opt != ARX_OPT_ADAGRAD && opt != ARX_OPT_SGD) return ARX_E_UNSUPPORTED;
-  if ((dim % 4) || dim > 128) return ARX_E_UNSUPPORTED;
+  if (dim % 4) return ARX_E_UNSUPPORTED;
   ApplyManyParams mp{};
   for (int i = 0; i < n_sets; ++i) {
     const arx_apply_set& q = sets[i];
@@ -1494,8 +1326,8 @@ extern "C" int arx_pool_bwd_apply_many(const arx_apply_set* sets, int n_sets, in
     mp.set[i].dout_stride = q.dout_stride; mp.set[i].plan = q.plan; mp.set[i].n_attr = q.n_attr;
   }
   mp.grad_scale = grad_scale_dev; mp.lr = lr; mp.n_sets = n_sets; mp.dim = dim; mp.opt = opt;
-  const int grid = arx_num_sms() * 2;          // persistent: 2 CTAs / SM, warps stride over the device-side row lists
-  pool_bwd_apply2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp);
+  const int grid = arx_num_sms() * g_tune_apply_cps;   // persistent: warps stride over the device-side row lists
+  pool_bwd_apply_many_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

@@ -183,9 +183,70 @@ def c4(a):
         % (d, mb, n_users, n_items), step, mb, 'interactions/s', a.steps, a.warmup, {'launch_mode': 'cuda graph replay'})
 
 
+def lstm_cell(a):
+    """The LSTM layer alone at the north-star shape (batch 4096, d = H = 128, T = 50): x-projection GEMM + the persistent
+    recurrence kernels (arx_lstm_seq_fwd / _bwd) + the three large weight / input gradient contractions; forward and
+    backward timed separately with CUDA events; `roofline` = dense tf32 FLOP/s of the whole layer step against half
+    the measured bf16 peak, `recurrence` = the two persistent kernels alone (they are HBM-bound on the gate tensors:
+    bytes = read x-projection + write gates + write h, c forward; read gates, c, dH + write dZ backward)."""
+    import arecsys_b200  # noqa: F401
+    from arecsys_b200 import _lib
+    from arecsys_b200.lstm.lstm_layer import LSTMLayer
+    T, mb, H = 50, a.mb or 4096, a.dim or 128
+    d_in = H
+    dev = torch.device('cuda:0')
+    rng = np.random.default_rng(0)
+    X = torch.tensor(rng.standard_normal((T, mb, d_in)).astype(np.float32), device=dev)
+    dO = torch.tensor(rng.standard_normal((T, mb, H)).astype(np.float32), device=dev)
+    W = (rng.standard_normal((d_in + H, 4 * H)) / np.sqrt(d_in + H)).astype(np.float32)
+    layer = LSTMLayer(d_in, H, dev, W=W, b=np.zeros(4 * H, np.float32))
+    res = {}
+    for seq in ('1', '0'):
+        os.environ['ARX_LSTM_SEQ'] = seq
+        for _ in range(a.warmup):
+            layer.forward(X, 1.0); layer.backward(dO)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        for _ in range(a.steps):
+            ev[0].record(); layer.forward(X, 1.0); ev[1].record(); layer.backward(dO); ev[2].record()
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1]); tb += ev[1].elapsed_time(ev[2])
+        res[seq] = (tf / a.steps, tb / a.steps)
+        if seq == '1':
+            _lib.timeline = []
+            layer.forward(X, 1.0); layer.backward(dO)
+            torch.cuda.synchronize()
+            tl, _lib.timeline = _lib.timeline, None
+            pk = timeline_table(_lib, tl, 1)
+    os.environ['ARX_LSTM_SEQ'] = '1'
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.isfile(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
+    tf32_peak = peaks.get('bf16_tflops_sustained', 1400.0) / 2
+    hbm = peaks.get('hbm_gbs', 6650.0)
+    fl_fwd = 2.0 * T * mb * (d_in + H) * 4 * H
+    fl_bwd = 2.0 * fl_fwd                                  # dX + dW_x, dh + dW_h
+    ms_f, ms_b = res['1']
+    rec = {}
+    for k, nbytes, fl in (('arx_lstm_seq_fwd', T * mb * (4 * H + 4 * H + 2 * H) * 4.0, 2.0 * T * mb * H * 4 * H),
+                          ('arx_lstm_seq_bwd', T * mb * (4 * H + 2 * H + H + 4 * H) * 4.0, 2.0 * T * mb * H * 4 * H)):
+        if k in pk:
+            us = pk[k]['avg_us']
+            rec[k] = {'us': us, 'us_per_time_step': us / T, 'hbm_gbs': nbytes / us / 1e3, 'hbm_frac': nbytes / us / 1e3 / hbm,
+                      'tf32_tflops': fl / us / 1e6, 'tensor_frac_of_tf32_peak': fl / us / 1e6 / tf32_peak,
+                      'ctas': (H // 32) * ((mb + 127) // 128)}
+    out = {'workload': 'LSTM layer: T=%d batch=%d d_in=H=%d, forward + backward (persistent cluster kernels)' % (T, mb, H),
+           'metric': 'targets/s (layer only)', 'value': T * mb / ((ms_f + ms_b) / 1e3), 'ms_fwd': ms_f, 'ms_bwd': ms_b,
+           'ms_fwd_per_step_kernels': res['0'][0], 'ms_bwd_per_step_kernels': res['0'][1],
+           'speedup_vs_per_step_path': (res['0'][0] + res['0'][1]) / (ms_f + ms_b), 'steps': a.steps, 'warmup': a.warmup,
+           'roofline': {'bound': 'tensor', 'achieved': (fl_fwd + fl_bwd) / ((ms_f + ms_b) / 1e3) / 1e12, 'peak': tf32_peak,
+                        'unit': 'TFLOP/s', 'frac': (fl_fwd + fl_bwd) / ((ms_f + ms_b) / 1e3) / 1e12 / tf32_peak,
+                        'peak_source': 'half of MEASURED_PEAKS.json bf16_tflops_sustained (tf32 operands)', 'traffic': None},
+           'recurrence': rec, 'per_kernel': pk}
+    print(json.dumps(out))
+
+
 if __name__ == '__main__':
     ap = argparse.ArgumentParser()
-    ap.add_argument('--workload', required=True, choices=['c3', 'c4', 'c5'])
+    ap.add_argument('--workload', required=True, choices=['c3', 'c4', 'c5', 'lstm_cell'])
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--n_users', type=int, default=0)
@@ -198,5 +259,5 @@ if __name__ == '__main__':
     if not torch.cuda.is_available():
         raise SystemExit('bench_extra.py needs a CUDA device (no CPU fallback)')
     t0 = time.time()
-    {'c3': c3, 'c4': c4, 'c5': c5}[a.workload](a)
+    {'c3': c3, 'c4': c4, 'c5': c5, 'lstm_cell': lstm_cell}[a.workload](a)
     print('[bench_extra] %s done in %.0fs' % (a.workload, time.time() - t0), file=sys.stderr)

@@ -41,6 +41,14 @@ __device__ __forceinline__ void st_cluster_f4(uint32_t caddr, float4 v) {
   asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(caddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+// 16-byte store into (possibly remote) shared memory that signals completion on an mbarrier of the DESTINATION CTA by
+// transaction bytes: data and signal travel together, so the producer needs no fence and no separate arrive (a
+// release-arrive at cluster scope compiles to MEMBAR.GPU, which also waits for every outstanding global store).
+__device__ __forceinline__ void st_async_f4(uint32_t caddr, float4 v, uint32_t cbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(caddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(cbar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(caddr) : "memory");
 }
@@ -128,7 +136,7 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     mbar_init(smem_u32(&w_full), 1);
     mbar_init(smem_u32(&zx_full), 1);
     mbar_init(smem_u32(&zx_empty), LS_EPI_WARPS);
-    mbar_init(smem_u32(&a_ready), NC * LS_EPI_WARPS);
+    mbar_init(smem_u32(&a_ready), 1);                       // one arrive (+ expect_tx) by the MMA thread; data by st.async bytes
     mbar_init(smem_u32(&acc_full), 1);
     mbar_init(smem_u32(&a_free), NC > 1 ? NC - 1 : 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -165,8 +173,9 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(LS_BM >> 4) << 24);
       mbar_wait(smem_u32(&w_full), 0);
       for (int t = 1; t < T; ++t) {
-        mbar_wait_cluster(smem_u32(&a_ready), (uint32_t)(t - 1) & 1u);     // h_{t-1}: all NC slices landed in sA
-        fence_async_proxy();
+        mbar_expect_tx(smem_u32(&a_ready), (uint32_t)KB * LS_SLAB);        // h_{t-1}: NC slices of 16 KB, sent with st.async
+        mbar_wait_cluster(smem_u32(&a_ready), (uint32_t)(t - 1) & 1u);
+        fence_async_smem();
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -198,9 +207,12 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
     float c[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) c[i] = 0.f;
-    uint32_t a_dst[NC];                                      // my 64-byte h segment inside every CTA's sA
+    uint32_t a_dst[NC], a_bar[NC];                           // my 64-byte h segment inside every CTA's sA, and its barrier
 #pragma unroll
-    for (int r = 0; r < NC; ++r) a_dst[r] = map_to_cta(smem_u32(sA + rank * LS_SLAB + rt * 128), (uint32_t)r);
+    for (int r = 0; r < NC; ++r) {
+      a_dst[r] = map_to_cta(smem_u32(sA + rank * LS_SLAB + rt * 128), (uint32_t)r);
+      a_bar[r] = map_to_cta(smem_u32(&a_ready), (uint32_t)r);
+    }
 
     for (int t = 0; t < T; ++t) {
       // x-projection (+ bias) of my 4 x 16 gate columns from the TMA-staged, 128-byte-swizzled tile
@@ -248,6 +260,19 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         h[i] = tf32_rn(go * fast_tanh(c[i]));                // h only feeds tensor-core contractions: kept tf32-exact
         z[0][i] = gi; z[1][i] = gj; z[2][i] = gf; z[3][i] = go;
       }
+      if (t + 1 < T) {
+        // h_t -> the A tile of every CTA of the cluster (k block = my rank, 16-byte chunks uh*4 .. uh*4+3), BEFORE the
+        // HBM stores below: the exchange is on the recurrence's critical path, the stores are not
+        if (NC > 1 && t > 0) mbar_wait_cluster(smem_u32(&a_free), (uint32_t)(t - 1) & 1u);   // peers' MMAs of step t retired
+#pragma unroll
+        for (int r = 0; r < NC; ++r) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 v = row_ok ? make_float4(h[c4 * 4], h[c4 * 4 + 1], h[c4 * 4 + 2], h[c4 * 4 + 3]) : f4_zero();
+            st_async_f4(a_dst[r] + (uint32_t)(((uh * 4 + c4) ^ (rt & 7)) << 4), v, a_bar[r]);
+          }
+        }
+      }
       if (row_ok) {
         float* gdst = p.G + ((size_t)t * p.mb + row) * (4 * H) + ucol;
 #pragma unroll
@@ -261,24 +286,6 @@ lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_cons
         for (int c4 = 0; c4 < 4; ++c4) {
           st_f4(hdst + c4 * 4, make_float4(h[c4 * 4], h[c4 * 4 + 1], h[c4 * 4 + 2], h[c4 * 4 + 3]));
           st_f4(cdst + c4 * 4, make_float4(c[c4 * 4], c[c4 * 4 + 1], c[c4 * 4 + 2], c[c4 * 4 + 3]));
-        }
-      }
-      if (t + 1 < T) {
-        // h_t -> the A tile of every CTA of the cluster (k block = my rank, 16-byte chunks uh*4 .. uh*4+3)
-        if (NC > 1 && t > 0) mbar_wait_cluster(smem_u32(&a_free), (uint32_t)(t - 1) & 1u);   // peers' MMAs of step t retired
-#pragma unroll
-        for (int r = 0; r < NC; ++r) {
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 v = row_ok ? make_float4(h[c4 * 4], h[c4 * 4 + 1], h[c4 * 4 + 2], h[c4 * 4 + 3]) : f4_zero();
-            st_cluster_f4(a_dst[r] + (uint32_t)(((uh * 4 + c4) ^ (rt & 7)) << 4), v);
-          }
-        }
-        fence_async_proxy();                                  // generic-proxy writes -> visible to tcgen05.mma
-        __syncwarp();
-        if (lane == 0) {
-#pragma unroll
-          for (int r = 0; r < NC; ++r) mbar_arrive_cluster(map_to_cta(smem_u32(&a_ready), (uint32_t)r));
         }
       }
     }
@@ -319,8 +326,8 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
     mbar_init(smem_u32(&w_full), 1);
     mbar_init(smem_u32(&a_ready), LS_EPI_WARPS);
     mbar_init(smem_u32(&acc_full), 1);
-    mbar_init(smem_u32(&recv_full[0]), NC > 1 ? (NC - 1) * LS_EPI_WARPS : 1);
-    mbar_init(smem_u32(&recv_full[1]), NC > 1 ? (NC - 1) * LS_EPI_WARPS : 1);
+    mbar_init(smem_u32(&recv_full[0]), 1);                  // one arrive (+ expect_tx) locally; data by st.async bytes
+    mbar_init(smem_u32(&recv_full[1]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_s), 128);
@@ -344,7 +351,7 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
       mbar_wait(smem_u32(&w_full), 0);
       for (int it = 0; it + 1 < T; ++it) {
         mbar_wait(smem_u32(&a_ready), (uint32_t)it & 1u);
-        fence_async_proxy();
+        fence_async_smem();
         tc_fence_after();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -399,19 +406,16 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
             const int slot = (int)rank - ((int)rank > r ? 1 : 0);          // my slot among r's NC-1 senders
             const uint32_t dst = map_to_cta(smem_u32(sR + ((size_t)(buf * (NC - 1) + slot) * LS_BM + rt) * LS_UC + uh * 16),
                                             (uint32_t)r);
+            const uint32_t dbar = map_to_cta(smem_u32(&recv_full[buf]), (uint32_t)r);
 #pragma unroll
             for (int c4 = 0; c4 < 4; ++c4)
-              st_cluster_f4(dst + c4 * 16, make_float4(a[c4 * 4], a[c4 * 4 + 1], a[c4 * 4 + 2], a[c4 * 4 + 3]));
+              st_async_f4(dst + c4 * 16, make_float4(a[c4 * 4], a[c4 * 4 + 1], a[c4 * 4 + 2], a[c4 * 4 + 3]), dbar);
           }
         }
         tc_fence_before();
         if (NC > 1) {
-          __syncwarp();
-          if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < NC; ++r)
-              if (r != (int)rank) mbar_arrive_cluster(map_to_cta(smem_u32(&recv_full[buf]), (uint32_t)r));
-          }
+          if (warp == 2 && lane == 0)                       // the peers' (NC - 1) x 16 KB partial tiles of this step
+            mbar_expect_tx(smem_u32(&recv_full[buf]), (uint32_t)(NC - 1) * LS_BM * LS_UC * 4u);
           mbar_wait_cluster(smem_u32(&recv_full[buf]), (uint32_t)((it - 1) >> 1) & 1u);
 #pragma unroll
           for (int s = 0; s < NC - 1; ++s) {                               // fixed sender order: deterministic
@@ -456,12 +460,6 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
             dz[0][i] = tf32_rn(g0); dz[1][i] = tf32_rn(g1); dz[2][i] = tf32_rn(g2); dz[3][i] = tf32_rn(g3);
           }
         }
-        float* gdst = p.G + rb * (4 * H) + ucol;
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4)
-            st_f4(gdst + g * H + c4 * 4, make_float4(dz[g][c4 * 4], dz[g][c4 * 4 + 1], dz[g][c4 * 4 + 2], dz[g][c4 * 4 + 3]));
       } else {
 #pragma unroll
         for (int g = 0; g < 4; ++g)
@@ -478,10 +476,18 @@ lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap map_w, const LstmSeqPara
             sts_f4(arow + (uint32_t)(((uh * 4 + c4) ^ (rt & 7)) << 4),
                    make_float4(dz[g][c4 * 4], dz[g][c4 * 4 + 1], dz[g][c4 * 4 + 2], dz[g][c4 * 4 + 3]));
         }
-        fence_async_proxy();
+        fence_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&a_ready));
+      }
+      if (row_ok) {                                           // dZ for the three large contractions: off the critical path
+        float* gdst = p.G + ((size_t)t * p.mb + row) * (4 * H) + ucol;
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4)
+            st_f4(gdst + g * H + c4 * 4, make_float4(dz[g][c4 * 4], dz[g][c4 * 4 + 1], dz[g][c4 * 4 + 2], dz[g][c4 * 4 + 3]));
       }
     }
   }

@@ -84,6 +84,10 @@ SIGNATURES = {
     'arx_pool_fwd_many': [vp, i32, i32, vp],
     'arx_mw_prep': [vp, vp, f32, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp],
+    'arx_gather_pairs': [vp, vp, vp, i64, vp, vp, vp],
+    'arx_cbow_window_batch': [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp],
+    'arx_lstm_pad_batch': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    'arx_gumbel_keys': [vp, i64, vp, vp, vp],
     'arx_lstm_seq_fwd': [vp, vp, vp, vp, i64, i64, i32, f32, vp],
     'arx_lstm_seq_bwd': [vp, vp, vp, vp, i64, i64, i32, vp],
     'arx_axpby_rows': [vp, vp, f32, f32, i64, i64, i32, vp, vp],

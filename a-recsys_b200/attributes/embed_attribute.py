@@ -730,7 +730,9 @@ class EmbeddingAttribute(object):
                     # the pooled bias is always the MEAN over attributes (:412), also in concat mode
                     biases.append((dbias / na).repeat_interleave(na) if mode == POOL_CONCAT else dbias)
         if len(rows) == 1:
-            arena = rows[0] if rows[0].is_contiguous() else rows[0].contiguous()
+            r0 = rows[0]
+            strided_ok = (r0.dim() == 2 and r0.stride(1) == 1 and r0.stride(0) % 4 == 0 and r0.data_ptr() % 16 == 0)
+            arena = r0 if (r0.is_contiguous() or strided_ok) else r0.contiguous()     # the kernels take a row stride
             bias = biases[0].contiguous() if any_bias else None
         else:
             arena = self._adjacent(rows)
@@ -894,8 +896,10 @@ class EmbeddingAttribute(object):
         for prefix, ids, mode, want_bias, kw in requests:
             a0, na = self.sets[prefix].attr_range(kw.get('no_id', False), kw.get('no_attribute', False))
             width = self.dim if mode == POOL_MEAN else self.dim * na
-            outs.append((torch.empty((ids.numel(), width), dtype=torch.float32, device=self.device),
-                         torch.empty((ids.numel(),), dtype=torch.float32, device=self.device) if want_bias else None))
+            o = kw.get('out')              # optional: pool straight into a (row-strided) view of a caller's buffer
+            if o is None:
+                o = torch.empty((ids.numel(), width), dtype=torch.float32, device=self.device)
+            outs.append((o, torch.empty((ids.numel(),), dtype=torch.float32, device=self.device) if want_bias else None))
         if (len(requests) > 1 and len(requests) <= 4 and self.dim in (128, 256)
                 and all(r[2] == POOL_MEAN for r in requests) and os.environ.get('ARX_POOL_MANY', '1') == '1'):
             # all lookups of the step in ONE launch (arx_pool_fwd_many): one ramp, one tail, balanced waves
@@ -920,7 +924,8 @@ class EmbeddingAttribute(object):
                 side.wait_stream(main)
                 forks.append(side)
             with torch.cuda.stream(side if side is not None else main):
-                res.append(self.pool(prefix, ids, mode, want_bias, out=o, bias_out=b, **kw))
+                res.append(self.pool(prefix, ids, mode, want_bias, out=o, bias_out=b,
+                                     **{k_: v_ for k_, v_ in kw.items() if k_ != 'out'}))
         for side in forks:
             main.wait_stream(side)
         return res

@@ -1,8 +1,10 @@
-"""read_data: raw TSVs -> (interactions, Attributes, index maps), cached by pickle in data_dir
-(reference: attributes/input_attribute.py:10-71)."""
+"""read_data: raw TSVs -> (interactions, Attributes, index maps), cached in data_dir
+(reference: attributes/input_attribute.py:10-71).  The cache is the `.npy` + manifest store of attribute_store.py
+(memory-mapped on load); a reference-style pickle `data_dir/data` is still read when it is all there is."""
 import os
 import pickle
 
+from . import attribute_store
 from .comb_attribute import HET, MIX
 from ..utils.load_data import load_raw_data
 from ..utils.preprocess import pickle_save
@@ -14,7 +16,12 @@ def read_data(raw_data_dir='../raw_data/data/', data_dir='../cache/data/', combi
     if not mylog:
         mylog = print
     data_filename = os.path.join(data_dir, 'data')
-    if os.path.isfile(data_filename):
+    if attribute_store.store_exists(data_dir):
+        mylog("attribute store {} exists! loading cached data (memory-mapped). \nCaution: change cached data dir "
+              "(--data_dir) if new data (or new preprocessing) is used.".format(os.path.join(data_dir, 'store')))
+        (data_tr, data_va, u_attr, i_attr, item_ind2logit_ind, logit_ind2item_ind, user_index,
+         item_index) = attribute_store.load_store(data_dir)
+    elif os.path.isfile(data_filename):
         mylog("data file {} exists! loading cached data. \nCaution: change cached data dir (--data_dir) "
               "if new data (or new preprocessing) is used.".format(data_filename))
         with open(data_filename, 'rb') as f:
@@ -44,7 +51,7 @@ def read_data(raw_data_dir='../raw_data/data/', data_dir='../cache/data/', combi
             u_attr, i_attr, item_ind2logit_ind, logit_ind2item_ind = mix.get_attributes(
                 users2, items2, data_tr, user_features, item_features)
         mylog("saving data format to data directory")
-        pickle_save((data_tr, data_va, u_attr, i_attr, item_ind2logit_ind, logit_ind2item_ind, user_index,
-                     item_index), data_filename)
+        attribute_store.save_store(data_dir, data_tr, data_va, u_attr, i_attr, item_ind2logit_ind, logit_ind2item_ind,
+                                   user_index, item_index)
     mylog('length of item_ind2logit_ind: {}'.format(len(item_ind2logit_ind)))
     return (data_tr, data_va, u_attr, i_attr, item_ind2logit_ind, logit_ind2item_ind, user_index, item_index)

@@ -6,6 +6,7 @@
 //   arx_mw_post : du0 = (dU + dts * Pt) * mask / keep ; dPt = dts * u
 //                 (was arx_rowdot_bwd + arx_scale_mask)
 #include "arx_common.cuh"
+#include "philox.cuh"
 
 namespace {
 
@@ -17,29 +18,11 @@ __device__ __forceinline__ float tf32_round(float x) {
   return __uint_as_float(u & 0xffffe000u);
 }
 
-// Philox-4x32-10 (Salmon et al., SC'11): counter-based, so the dropout mask needs no generator state on the host and
-// the captured CUDA graph draws a fresh mask on every replay (key = seed, counter = (step, element / 4)).
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t out[4]) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
 // tf.nn.dropout keeps an element when floor(keep + U[0,1)) == 1, i.e. with probability keep
 __device__ __forceinline__ float dropout_keep(const unsigned long long* rng, long long elem, float keep) {
-  const unsigned long long seed = rng[0], step = rng[1];
   uint32_t o[4];
-  const unsigned long long ctr = (unsigned long long)elem >> 2;
-  philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)seed,
-                (uint32_t)(seed >> 32), o);
-  const float u = (float)(o[elem & 3] >> 8) * (1.0f / 16777216.0f);          // [0, 1)
-  return floorf(keep + u);
+  philox_words(rng, (unsigned long long)elem >> 2, o);
+  return floorf(keep + u01(o[elem & 3]));
 }
 
 constexpr int kPrepRows = 32;

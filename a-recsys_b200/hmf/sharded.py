@@ -42,19 +42,23 @@ class ShardedLatentProductModel(LatentProductModel):
         S = m.sampled_ids.numel()
         pre = m._out_prefix()
         # ---- forward: partial pooling of owned rows, one RS + one AR --------------------------
-        fwd = torch.empty((n_g, 2 * d + 1), dtype=torch.float32, device=dev)
+        # one packed exchange buffer per collective; row pitch 2d + 4 keeps every block 16-byte aligned so that the
+        # lookups pool STRAIGHT into it (no staging copies): [ user vector | target-item vector | target bias, pad ]
+        W = 2 * d + 4
+        fwd = torch.empty((n_g, W), dtype=torch.float32, device=dev)
+        sp = torch.empty((S, d + 4), dtype=torch.float32, device=dev)
         irng0 = m.sets[pre].attr_range()
         # the backward plans depend on the ids only: build them on side streams under the forward pass
         m.prefetch_plans({'user': [(m.sets['user'].attr_range(), users_g, POOL_MEAN)],
                           pre: [(irng0, m.sampled_ids, POOL_MEAN), (irng0, items_g, POOL_MEAN)]})
         (pu, _, urng), (pt, bt, irng), (ps, bs, _) = m.pool_many([
-            ('user', users_g, POOL_MEAN, False, {}),
-            (pre, items_g, POOL_MEAN, True, {}),
-            (pre, m.sampled_ids, POOL_MEAN, True, {})])
-        fwd[:, :d] = pu
-        fwd[:, d:2 * d] = pt
+            ('user', users_g, POOL_MEAN, False, {'out': fwd[:, :d]}),
+            (pre, items_g, POOL_MEAN, True, {'out': fwd[:, d:2 * d]}),
+            (pre, m.sampled_ids, POOL_MEAN, True, {'out': sp[:, :d]})])
         fwd[:, 2 * d] = bt
-        sp = torch.cat([ps, bs[:, None]], 1)
+        fwd[:, 2 * d + 1:] = 0
+        sp[:, d] = bs
+        sp[:, d + 1:] = 0
         loc = ex.reduce_scatter_rows(fwd)
         sp = ex.all_reduce(sp)
         U0 = loc[:, :d].contiguous()
@@ -64,32 +68,75 @@ class ShardedLatentProductModel(LatentProductModel):
         bsl = sp[:, d].contiguous()
         users_l = users_g[r * mb:(r + 1) * mb].contiguous()
         keep = self.dropout
-        u = m.dropout(U0, keep, masks[0] if masks else None)
-        dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
-        tscore = torch.empty((mb,), dtype=torch.float32, device=dev)
-        call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), btl.data_ptr(), mb, d, tscore.data_ptr())
         scale = self._scale(n_g)[:mb]                                   # 1 / (G*mb): global batch mean
-        fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l)
-        if fused is not None:                                           # scoring + WMRB + adjoints on the tensor cores
+        if _lib.ce_supported(mb, S, d) and d % 4 == 0:
+            # fused glue of the single-GPU step (arx_mw_prep / arx_mw_post): dropout (mask injected, or drawn in the
+            # kernel by Philox) + tf32 rounding + transposes + target score in one launch, the two adjoints in another
+            f32 = dict(dtype=torch.float32, device=dev)
+            u = torch.empty((mb, d), **f32); U_r = torch.empty((mb, d), **f32); UT = torch.empty((d, mb), **f32)
+            P_r = torch.empty((S, d), **f32); PT = torch.empty((d, S), **f32)
+            tscore = torch.empty((mb,), **f32)
+            inv_keep = 1.0 / keep
+            dmask = drng = dmask_out = None
+            if keep != 1.0:
+                if masks:
+                    dmask = masks[0]
+                else:
+                    if not hasattr(self, '_drop_rng'):
+                        seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) + 7919 * r        # a different stream per rank
+                        self._drop_rng = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+                    drng = self._drop_rng
+                    dmask_out = torch.empty((mb, d), **f32)
+            call('arx_mw_prep', U0.data_ptr(), _lib.ptr(dmask), inv_keep, _lib.ptr(drng), _lib.ptr(dmask_out), Pt.data_ptr(),
+                 btl.data_ptr(), Ps.data_ptr(), mb, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), tscore.data_ptr(),
+                 P_r.data_ptr(), PT.data_ptr())
+            if drng is not None:
+                dmask = dmask_out
+            fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l, prepared=(U_r, P_r, UT, PT))
+            if fused is None:
+                raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
             bl, (dU, dPs, dbs, dts) = fused
+            loss_sum = (bl.sum() / n_g).reshape(1)
+            dU0 = torch.empty((mb, d), **f32)
+            dPt = torch.empty((mb, d), **f32)
+            call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), _lib.ptr(dmask), inv_keep, mb, d,
+                 dU0.data_ptr(), dPt.data_ptr(), _lib.ptr(drng))
         else:
-            logits = torch.empty((mb, S), dtype=torch.float32, device=dev)
-            _lib.gemm(u, Ps, logits, mb, S, d, 0, 1, bsl)
-            bl = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=True, pos_rows=users_l)
-            # ---- backward: one AR + one AG, then local sparse Adagrad ----------------------------
-            D, dts = logits, m._last_dtarget
-            dU, dPs, dbs = self._scores_backward(D, u, Ps)
-        loss_sum = (bl.sum() / n_g).reshape(1)
-        dPt = torch.empty_like(Pt)
-        call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, d, dU.data_ptr(), dPt.data_ptr())
-        if keep != 1.0:
-            dU0 = torch.empty_like(dU)
-            call('arx_scale_mask', dU.data_ptr(), dmask.data_ptr(), 1.0 / keep, dU.numel(), dU0.data_ptr())
-        else:
-            dU0 = dU
-        dsp = ex.all_reduce(torch.cat([dPs, dbs[:, None]], 1))
-        back = ex.all_gather_rows(torch.cat([dU0, dPt, dts[:, None]], 1))
-        m.push_grad('user', urng, users_g, POOL_MEAN, back[:, :d].contiguous())
+            u = m.dropout(U0, keep, masks[0] if masks else None)
+            dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
+            tscore = torch.empty((mb,), dtype=torch.float32, device=dev)
+            call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), btl.data_ptr(), mb, d, tscore.data_ptr())
+            fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l)
+            if fused is not None:                                           # scoring + WMRB + adjoints on the tensor cores
+                bl, (dU, dPs, dbs, dts) = fused
+            else:
+                logits = torch.empty((mb, S), dtype=torch.float32, device=dev)
+                _lib.gemm(u, Ps, logits, mb, S, d, 0, 1, bsl)
+                bl = m.compute_loss(logits, tscore, 'mw', row_scale=scale, want_grad=True, pos_rows=users_l)
+                # ---- backward: one AR + one AG, then local sparse Adagrad ----------------------------
+                D, dts = logits, m._last_dtarget
+                dU, dPs, dbs = self._scores_backward(D, u, Ps)
+            loss_sum = (bl.sum() / n_g).reshape(1)
+            dPt = torch.empty_like(Pt)
+            call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, d, dU.data_ptr(), dPt.data_ptr())
+            if keep != 1.0:
+                dU0 = torch.empty_like(dU)
+                call('arx_scale_mask', dU.data_ptr(), dmask.data_ptr(), 1.0 / keep, dU.numel(), dU0.data_ptr())
+            else:
+                dU0 = dU
+        dsp_in = torch.empty((S, d + 4), dtype=torch.float32, device=dev)
+        dsp_in[:, :d] = dPs
+        dsp_in[:, d] = dbs
+        dsp_in[:, d + 1:] = 0
+        dsp = ex.all_reduce(dsp_in)
+        mine = torch.empty((mb, W), dtype=torch.float32, device=dev)
+        mine[:, :d] = dU0
+        mine[:, d:2 * d] = dPt
+        mine[:, 2 * d] = dts
+        mine[:, 2 * d + 1:] = 0
+        back = ex.all_gather_rows(mine)
+        # the gathered gradient rows are used in place (row-strided views: the kernels take a row pitch)
+        m.push_grad('user', urng, users_g, POOL_MEAN, back[:, :d])
         rng = m.sets[pre].attr_range()
         m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, dsp[:, :d].contiguous(), dsp[:, d].contiguous())
         m.push_grad(pre, rng, items_g, POOL_MEAN, back[:, d:2 * d].contiguous(), back[:, 2 * d].contiguous())

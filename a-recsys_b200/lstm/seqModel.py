@@ -197,10 +197,15 @@ class SeqModel(object):
         m.add_input({}, user_input, None, item_sampled=item_sampled, item_sampled_id2idx=item_sampled_id2idx,
                     forward_only=forward_only, recommend=recommend, loss=self.loss)
         users = m.u_indices['input']
-        item_ids = m._ids(np.asarray(item_inputs[:T], dtype=np.int32).reshape(-1))
-        tgt_items = m._ids(np.asarray(targets[:T], dtype=np.int32).reshape(-1))
+        # time-major lists [T][mb] as the reference feeds them, or [T, mb] device tensors (utils/device_batch.py)
+        as_ids = lambda x: (x[:T].reshape(-1) if isinstance(x, torch.Tensor) else np.asarray(x[:T], dtype=np.int32).reshape(-1))
+        item_ids = m._ids(as_ids(item_inputs))
+        tgt_items = m._ids(as_ids(targets))
         tgt = m.item2logit_dev[tgt_items.long()].contiguous()                 # target_mapping (:294)
-        w = torch.as_tensor(np.asarray(target_weights[:T], dtype=np.float32)).to(dev)     # [T, mb]
+        if isinstance(target_weights, torch.Tensor):
+            w = target_weights[:T].to(device=dev, dtype=torch.float32)
+        else:
+            w = torch.as_tensor(np.asarray(target_weights[:T], dtype=np.float32)).to(dev)     # [T, mb]
         row_scale = (w / (w.sum(0, keepdim=True) + 1e-12)).reshape(-1).contiguous()        # sequence_loss
         keep = 1.0 if forward_only else self.dropoutRate
         train = not forward_only

@@ -52,16 +52,42 @@ def positives_csr(users, items, n_users):
 
 
 class DeviceItemSampler(object):
-    """Draw n distinct items with P(order) as in np.random.choice(population, n, False, p)."""
+    """Draw n distinct items with P(order) as in np.random.choice(population, n, False, p) (utils/prepare_train.py:7-17):
+    Gumbel-top-k — key_i = log p_i - log(-log U_i) with U from the library's counter-based generator (arx_gumbel_keys), the
+    n largest keys selected by arx_topk_rows (radix select, n <= 1024).  Everything runs in libarx_b200.so on the current
+    stream: O(V) device work per refresh instead of np.random.choice's O(V) host work + a 10^6-10^7 element upload."""
+
+    CHUNKS = 128          # two-stage selection for large populations: top-n per chunk, then top-n of the candidates
 
     def __init__(self, item_population, p_item, device, seed=0):
+        from .. import _lib
+        self._lib = _lib
         self.population = torch.as_tensor(np.asarray(item_population, dtype=np.int32)).to(device)
-        self.logp = torch.log(torch.as_tensor(np.asarray(p_item, dtype=np.float64)).to(device)).float()
-        self.gen = torch.Generator(device=device)
-        self.gen.manual_seed(seed)
+        logp = torch.log(torch.as_tensor(np.asarray(p_item, dtype=np.float64))).float()
+        self.V = logp.numel()
+        self.C = self.CHUNKS if self.V >= (1 << 16) else 1
+        self.chunk = (self.V + self.C - 1) // self.C
+        pad = self.chunk * self.C - self.V
+        # padding entries have probability 0 (log p = -inf): never selected
+        self.logp = torch.cat([logp, torch.full((pad,), float('-inf'))]).to(device).contiguous()
+        self.keys = torch.empty_like(self.logp)
+        self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
 
     def sample(self, n):
-        u = torch.rand(self.logp.shape, generator=self.gen, device=self.logp.device).clamp_(1e-20, 1.0)
-        keys = self.logp - torch.log(-torch.log(u))
-        idx = torch.topk(keys, n).indices
-        return self.population[idx].contiguous()
+        if n > 1024 or n > self.V:
+            raise ValueError('DeviceItemSampler draws at most min(1024, population) items per call')
+        call, dev = self._lib.call, self.logp.device
+        call('arx_gumbel_keys', self.logp.data_ptr(), self.logp.numel(), self.rng.data_ptr(), self.keys.data_ptr())
+        if self.C == 1:
+            idx = torch.empty((1, n), dtype=torch.int32, device=dev)
+            call('arx_topk_rows', self.keys.data_ptr(), 1, self.V, self.V, n, idx.data_ptr(), None)
+            return self.population[idx[0].long()].contiguous()
+        k1 = min(n, self.chunk)
+        idx1 = torch.empty((self.C, k1), dtype=torch.int32, device=dev)
+        val1 = torch.empty((self.C, k1), dtype=torch.float32, device=dev)
+        call('arx_topk_rows', self.keys.data_ptr(), self.C, self.chunk, self.chunk, k1, idx1.data_ptr(), val1.data_ptr())
+        idx2 = torch.empty((1, n), dtype=torch.int32, device=dev)
+        call('arx_topk_rows', val1.data_ptr(), 1, self.C * k1, self.C * k1, n, idx2.data_ptr(), None)
+        j = idx2[0].long()
+        glob = (j // k1) * self.chunk + idx1.reshape(-1)[j].long()
+        return self.population[glob].contiguous()

@@ -166,9 +166,21 @@ def train():
         torch_prof = torch.profiler.profile(activities=[torch.profiler.ProfilerActivity.CPU,
                                                         torch.profiler.ProfilerActivity.CUDA])
         torch_prof.__enter__()
+    # Batches assembled on the device (utils/device_batch.py): the same interaction stream as model.get_batch /
+    # get_permuted_batch under the same seeds (Python's / NumPy's generators are consumed identically), as device tensors.
+    # ARX_DEVICE_BATCH=0 keeps the reference's per-example Python loop.
+    device_sampler = None
+    if os.environ.get('ARX_DEVICE_BATCH', '1') == '1':
+        from arecsys_b200.utils.device_batch import DeviceInteractionSampler
+        device_sampler = DeviceInteractionSampler(data_tr, batch_size, model.device,
+                                                  'permute' if FLAGS.sample_type == 'permute' else 'random')
     while True:
         start_time = time.time()
-        (user_input, item_input, neg_item_input) = get_next_batch(data_tr)
+        if device_sampler is not None:
+            user_input, item_input = device_sampler.next()
+            neg_item_input = None
+        else:
+            (user_input, item_input, neg_item_input) = get_next_batch(data_tr)
         if loss_func in ['mw', 'mce'] and current_step % FLAGS.n_resample == 0:
             item_sampled, item_sampled_id2idx = sample_items(item_population, FLAGS.n_sampled, p_item)
         else:

@@ -352,6 +352,30 @@ int arx_axpby_rows(const float* x1, const float* x2_rows, float a, float b, int6
 int arx_sum_over_steps(const float* x, int64_t T, int64_t rep, int dim, float scale, float* out,
                        void* stream);
 
+/* SURVEY 8(f) row 1 — batch assembly and negative-pool sampling on the device (integer gathers; the draws that decide
+ * WHICH examples go into a batch stay where the reference has them, or use the counter-based generator below).
+ * rng_state: device uint64[2] = {seed, step}; every call that draws advances `step` (Philox-4x32-10).
+ *   arx_gather_pairs      : LatentProductModel.get_batch / get_permuted_batch (hmf/hmf_model.py:230-260) for given
+ *                           interaction indices: out_users[b] = users[idx[b]], out_items[b] = items[idx[b]].
+ *   arx_cbow_window_batch : DataIterator.get_next_cbow (word2vec/data_iterator.py:108-169): slot b = the (cursor + b)-th
+ *                           non-PAD stream event; ni inputs from the `window` preceding stream positions (distinct when the
+ *                           user already has >= ni events in the window).  out_inputs [ni, mb].  window, ni <= 64.
+ *   arx_lstm_pad_batch    : SeqModel.get_batch (lstm/seqModel.py:356-404) for given sequence indices sel[b] (-1 = empty
+ *                           slot) over a CSR of sequences: time-major inputs / targets / weights [T, mb].
+ *   arx_gumbel_keys       : keys[i] = log p[i] - log(-log U_i); the n largest (arx_topk_rows) are a draw without
+ *                           replacement with probabilities p = np.random.choice(items, n, False, p)
+ *                           (utils/prepare_train.py:7-17). */
+int arx_gather_pairs(const int32_t* users, const int32_t* items, const int64_t* idx, int64_t n, int32_t* out_users,
+                     int32_t* out_items, void* stream);
+int arx_cbow_window_batch(const int32_t* users, const int32_t* items, const int32_t* u_seq_len, const int64_t* targets,
+                          int64_t l_seq, int64_t n_targets, int64_t cursor, int mb, int ni, int window,
+                          uint64_t* rng_state, int32_t* out_users, int32_t* out_inputs, int32_t* out_targets,
+                          void* stream);
+int arx_lstm_pad_batch(const int64_t* seq_ptr, const int32_t* seq_items, const int32_t* seq_users, const int64_t* sel,
+                       int mb, int T, int start_id, int pad_id, int user_pad_id, int32_t* out_users,
+                       int32_t* out_inputs, int32_t* out_targets, float* out_weights, void* stream);
+int arx_gumbel_keys(const float* logp, int64_t n, uint64_t* rng_state, float* keys, void* stream);
+
 /* K10 — tf.nn.top_k(sorted=True) over materialised scores (hmf/hmf_model.py:154):
  * descending, ties -> lower index. idx_out [mb,k] int32, val_out [mb,k] or NULL. */
 int arx_topk_rows(const float* scores, int64_t mb, int64_t V, int64_t ld, int k,

@@ -54,7 +54,7 @@ def test_read_data_reproduces_fixture(tmp_path):
     # cache hit returns the same objects' content
     again = read_data(REF_DATA, str(tmp_path / 'c'), 'mix', 3100, 2, mylog=lambda s: None)
     assert np.array_equal(again[2].features_mulhot[0], ua.features_mulhot[0]) and again[4] == i2l
-    assert os.path.isfile(tmp_path / 'c' / 'item_vocab0_500000') and os.path.isfile(tmp_path / 'c' / 'data')
+    assert os.path.isfile(tmp_path / 'c' / 'item_vocab0_500000') and os.path.isfile(tmp_path / 'c' / 'store' / 'manifest.json')
 
 
 def _mini(tmp_path, with_types=True):
@@ -133,3 +133,33 @@ def test_sampling_helpers():
     assert sorted(tr[0]) == [5, 9] and va == {0: [7]}
     ptr, it = prepare_train.positives_csr([0, 1, 2, 0, 0], [5, 5, 7, 9, 5], 4)
     assert ptr.tolist() == [0, 2, 3, 4, 4] and it.tolist() == [5, 9, 5, 7]
+
+
+def test_attribute_store_roundtrip_and_mmap(tmp_path):
+    """the `.npy` + manifest store is an exact inverse pair, loads memory-mapped, and read_data's cache
+    hit goes through it (no pickle of Python lists)."""
+    from arecsys_b200.attributes import attribute_store
+    from arecsys_b200.utils import synthetic
+    ua, ia, i2l, l2i = synthetic.make_dataset(300, 200, 3, 50, 4, 9, seed=3, logit_size=150)
+    i2l_d = {int(l2i[v]): v for v in range(len(l2i))}
+    l2i_d = {v: int(l2i[v]) for v in range(len(l2i))}
+    data_tr = [(1, 2, 0), (5, 7, 11), (299, 149, 3)]
+    data_va = [(4, 4, 9)]
+    uidx = {'u%d' % k: k for k in range(300)}
+    iidx = {1000 + k: k for k in range(200)}                      # int raw ids keep their type
+    d = attribute_store.save_store(str(tmp_path), data_tr, data_va, ua, ia, i2l_d, l2i_d, uidx, iidx)
+    assert attribute_store.store_exists(str(tmp_path)) and os.path.isfile(os.path.join(d, 'i_mul_0_values.npy'))
+    tr, va, ua2, ia2, i2l2, l2i2, uidx2, iidx2 = attribute_store.load_store(str(tmp_path))
+    assert tr == data_tr and va == data_va and i2l2 == i2l_d and l2i2 == l2i_d and uidx2 == uidx and iidx2 == iidx
+    for a, b in ((ua, ua2), (ia, ia2)):
+        assert a.num_features_cat == b.num_features_cat and a.num_features_mulhot == b.num_features_mulhot
+        assert a._embedding_classes_list_cat == b._embedding_classes_list_cat
+        assert a._embedding_classes_list_mulhot == b._embedding_classes_list_mulhot
+        for x, y in zip(a.features_cat + a.features_mulhot + a.mulhot_starts + a.mulhot_lengths,
+                        b.features_cat + b.features_mulhot + b.mulhot_starts + b.mulhot_lengths):
+            assert isinstance(y, np.memmap) and y.dtype == np.int32 and np.array_equal(x, y)
+    for x, y in zip(ia.full_cat_tr + ia.full_values_tr + ia.full_segids_tr + ia.full_lengths_tr,
+                    ia2.full_cat_tr + ia2.full_values_tr + ia2.full_segids_tr + ia2.full_lengths_tr):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+    ia2.set_model_size(8)                                           # a loaded container behaves like a built one
+    assert ia2.num_entities == ia.num_entities

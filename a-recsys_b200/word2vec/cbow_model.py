@@ -16,6 +16,9 @@ from ..hmf.hmf_model import _Var, _Saver
 
 
 class Model(object):
+    # skip-gram (word2vec/skipgram_model.py:86-88) trains on the FIRST input item only; its test tower is CBOW's
+    train_first_input_only = False
+
     def __init__(self, user_size, item_size, size, batch_size, learning_rate, learning_rate_decay_factor,
                  user_attributes=None, item_attributes=None, item_ind2logit_ind=None, logit_ind2item_ind=None,
                  n_input_items=0, loss_function='ce', logit_size_test=None, dropout=1.0, top_N_items=100,
@@ -68,6 +71,8 @@ class Model(object):
         """linear_seq.py:70-120.  item_input: [ni][mb] lists (time-major), item_output: [mb]."""
         m = self.att_emb
         ni = self.n_input
+        if self.train_first_input_only and not (forward_only or recommend):
+            ni = 1
         m.add_input({}, user_input, None, item_sampled=item_sampled, item_sampled_id2idx=item_sampled_id2idx,
                     forward_only=forward_only, recommend=recommend, loss=loss)
         users = m.u_indices['input']

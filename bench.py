@@ -199,7 +199,7 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    cfg = {'workload': 'C2: HMF dim=%d batch=%d synthetic %d users / %d items, per side id + %d multi-hot attrs '
+    cfg = {'workload': ('C4' if a.n_items >= 10000000 else 'C2') + ': HMF dim=%d batch=%d synthetic %d users / %d items, per side id + %d multi-hot attrs '
                        '(mean bag %d, vocab %d, Zipf 1.05), loss=%s%s, keep_prob=%.2f, Adagrad' % (
                            a.dim, a.mb, a.n_users, a.n_items, a.n_mulhot, a.mean_len, a.vocab_m, a.loss,
                            (' n_sampled=%d n_resample=%d' % (a.n_sampled, a.n_resample)) if a.loss == 'mw' else '',

@@ -420,9 +420,10 @@ class TorchRefCbow(TorchRefSeq):
     """word2vec/cbow_model.py:76-136 restated with autograd: h = dropout(mean(user, mean_k item_k)),
     literal get_prediction over the (separate) output tables, loss, Adagrad."""
 
-    def __init__(self, *a, ni=2, **kw):
+    def __init__(self, *a, ni=2, sg=False, **kw):
         super(TorchRefCbow, self).__init__(*a, **kw)
         self.ni = ni
+        self.sg = sg          # skip-gram (word2vec/skipgram_model.py:86-88): the TRAINING tower sees input 0 only
 
     def recommend(self, users, item_inputs, k):
         """top-k logit indices of logits_test (cbow_model.py:95-104,138-139): no dropout, user embedding alone
@@ -446,7 +447,8 @@ class TorchRefCbow(TorchRefSeq):
         def fwd():
             self.slices = []
             ue = self._emb('user', self.ua, users, False)
-            its = torch.stack([self._emb('item', self.ia, item_inputs[k], False) for k in range(n_input)], 0).mean(0)
+            n_in = 1 if (self.sg and not forward_only) else n_input
+            its = torch.stack([self._emb('item', self.ia, item_inputs[k], False) for k in range(n_in)], 0).mean(0)
             if forward_only and self.ni == 0:
                 x = ue
             else:

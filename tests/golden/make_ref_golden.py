@@ -407,11 +407,17 @@ CBOW_CASES = {
     'warp_sep_ni3': ('warp', True, 3),
     'bbpr_shared_ni1': ('bbpr', False, 1),
     'ce_shared_ni0': ('ce', False, 0),
+    # skip-gram tower (word2vec/skipgram_model.py: trains on the first input item only), fixtures ref_cbow_sg_*
+    'sg_ce_sep_ni2': ('ce', True, 2),
+    'sg_warp_shared_ni1': ('warp', False, 1),
 }
 
 
 def run_cbow_case(name, n_steps=4):
-    import cbow_model as ref_cbow         # /root/reference/word2vec/cbow_model.py
+    if name.startswith('sg_'):
+        import skipgram_model as ref_cbow     # /root/reference/word2vec/skipgram_model.py
+    else:
+        import cbow_model as ref_cbow         # /root/reference/word2vec/cbow_model.py
     loss, sep, ni = CBOW_CASES[name]
     dim, mb, n_users, n_items, lr, keep, topn = 8, 16, 40, 30, 0.5, 0.5, 5
     ua, ia, _, l2i = small_dataset(n_users, n_items, 2, 15, 3, 5, 0, None, dim)

@@ -426,3 +426,25 @@ def test_het_mix_pipeline_matches_reference_on_ml1m(tmp_path, py2, comb, logits)
         sys.modules.update(saved_mods)
         for m in ('preprocess', 'comb_attribute', 'attribute', 'cPickle'):
             sys.modules.pop(m, None)
+
+
+def test_skipgram_pair_generator_matches_reference(py2):
+    """word2vec/data_iterator.py::get_next_sg (:60-106) under the same np.random seed: identical (user, input, output)
+    pairs batch by batch — the port consumes the generator exactly like the reference."""
+    ref = _load(os.path.join(REF, 'word2vec', 'data_iterator.py'), 'ref_w2v_iter_sg')
+    from arecsys_b200.word2vec.data_iterator import DataIterator as Ours
+    rng = np.random.default_rng(4)
+    PAD = 999
+    seq = []
+    for u in range(31):
+        seq.append((u, PAD))
+        seq.extend((u, int(v)) for v in rng.integers(0, 500, int(rng.integers(1, 14))))
+    for mb, n_skips, window in ((8, 3, 2), (16, 2, 5), (7, 1, 1)):
+        np.random.seed(3)
+        a = ref.DataIterator(seq, PAD, mb, n_skips, window, False).get_next_sg()
+        ra = [tuple(np.asarray(x).copy() if not isinstance(x, list) else np.asarray(x[0]).copy() for x in next(a)) for _ in range(30)]
+        np.random.seed(3)
+        b = Ours(seq, PAD, mb, n_skips, window, False).get_next_sg()
+        for step in range(30):
+            ub, ib, ob = next(b)
+            assert np.array_equal(ra[step][0], ub) and np.array_equal(ra[step][1], ib[0]) and np.array_equal(ra[step][2], ob), (mb, step)

@@ -264,6 +264,7 @@ class CbowCase(object):
         d = np.load(os.path.join(GOLD, 'ref_cbow_%s.npz' % name))
         self.d = d
         self.loss, self.sep, self.ni = str(d['loss']), bool(d['sep']), int(d['ni'])
+        self.sg = name.startswith('sg_')        # fixtures of the reference's skipgram_model.py
         self.dim, self.mb, self.n_users, self.n_items = int(d['dim']), int(d['mb']), int(d['n_users']), int(d['n_items'])
         self.lr, self.keep, self.top_n, self.n_steps = float(d['lr']), float(d['keep_prob']), int(d['top_n']), int(d['n_steps'])
         self.ua = _attributes(d, 'u_', self.dim)
@@ -293,7 +294,7 @@ def test_oracle_reproduces_reference_cbow_run(name):
     c = CbowCase(name)
     ref = TorchRefCbow(c.ua, c.ia, {k: v.copy() for k, v in c.params.items()}, c.l2i_d, c.i2l_d, loss=c.loss,
                        keep_prob=c.keep, learning_rate=c.lr, n_sampled=None, dtype=torch.float64, size=c.dim,
-                       item_output=c.sep, ni=c.ni)
+                       item_output=c.sep, ni=c.ni, sg=c.sg)
     for it in range(c.n_steps):
         users, ins, outs, mask, pos = c.batch(it)
         ref.pos, ref.pos_eval = pos, pos
@@ -314,8 +315,11 @@ def test_oracle_reproduces_reference_cbow_run(name):
 def test_cuda_path_reproduces_reference_cbow_run(cuda, name, exact):
     import torch
     from arecsys_b200 import _lib
-    from arecsys_b200.word2vec.cbow_model import Model
     c = CbowCase(name)
+    if c.sg:
+        from arecsys_b200.word2vec.skipgram_model import Model
+    else:
+        from arecsys_b200.word2vec.cbow_model import Model
     ltol, ptol = (2e-4, 2e-3) if exact else (2e-3, 2e-2)
     _lib.exact_fp32 = exact
     try:

@@ -36,7 +36,10 @@ KEYS = [('gpu__time_duration.sum', 'duration'),
         ('smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio', 'stall long scoreboard'),
         ('smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'stall short scoreboard'),
         ('smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'stall barrier'),
-        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'stall wait')]
+        ('smsp__average_warps_issue_stalled_wait_per_issue_active.ratio', 'stall wait'),
+        ('smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio', 'stall lg throttle'),
+        ('smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio', 'stall mio throttle'),
+        ('smsp__average_warps_issue_stalled_membar_per_issue_active.ratio', 'stall membar')]
 
 
 def short(name):
@@ -70,7 +73,10 @@ def launches(path, out, cmd):
 
 
 def full(rep, out, cmd, traffic=None):
-    txt = subprocess.check_output(['ncu', '-i', rep, '--page', 'raw', '--csv'], stderr=subprocess.DEVNULL).decode(errors='replace')
+    if rep.endswith('.csv'):          # already exported on the GPU box: `ncu -i rep --page raw --csv > file.csv`
+        txt = open(rep, errors='replace').read()
+    else:
+        txt = subprocess.check_output(['ncu', '-i', rep, '--page', 'raw', '--csv'], stderr=subprocess.DEVNULL).decode(errors='replace')
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ix = {h: i for i, h in enumerate(hdr)}

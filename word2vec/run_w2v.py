@@ -130,6 +130,8 @@ def create_model(session, u_attributes=None, i_attributes=None, item_ind2logit_i
     n_sampled = FLAGS.n_sampled if FLAGS.loss in ['mw', 'mce'] else None
     if FLAGS.model == 'cbow':
         from arecsys_b200.word2vec import cbow_model as w2v_model
+    elif FLAGS.model == 'sg':
+        from arecsys_b200.word2vec import skipgram_model as w2v_model          # run_w2v.py:202-203
     else:
         mylog('not implemented error')
         exit(1)
@@ -167,7 +169,10 @@ def train(raw_data=None):
     if FLAGS.loss in ['warp', 'mw', 'bbpr']:
         model.prepare_warp(*positive_items(data_tr, data_va))
     np.random.seed(0)
-    ite = DataIterator(seq_tr, end_ind, FLAGS.batch_size, max(FLAGS.ni, 1), FLAGS.skip_window, False).get_next_cbow()
+    if FLAGS.model == 'sg':                                                     # run_w2v.py:259-266
+        ite = DataIterator(seq_tr, end_ind, FLAGS.batch_size, FLAGS.num_skips, FLAGS.skip_window, False).get_next_sg()
+    else:
+        ite = DataIterator(seq_tr, end_ind, FLAGS.batch_size, max(FLAGS.ni, 1), FLAGS.skip_window, False).get_next_cbow()
     mylog('started training')
     step_time, loss, current_step = 0.0, 0.0, 0
     patience = FLAGS.patience

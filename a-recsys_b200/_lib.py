@@ -46,6 +46,7 @@ class ApplySet(ctypes.Structure):
 
 POOL_MEAN, POOL_CONCAT = 0, 1
 OPT_ADAGRAD, OPT_SGD, OPT_NONE = 0, 1, 2
+HEAVY_DEFAULT = 64          # default of arx_set_tuning("heavy"): keep in step with g_tune_heavy in csrc/pool.cu
 LOSS_KIND = {'ce': 0, 'warp': 1, 'warp_eval': 1, 'rs': 2, 'rs-sig': 3, 'rs-sig2': 4, 'bbpr': 5, 'mw': 6}
 LOSS_FUNC = {'log': 0, 'exp': 1, 'poly': 2, 'poly2': 3, 'linear': 4, 'square': 5}
 
@@ -84,6 +85,10 @@ SIGNATURES = {
     'arx_pool_fwd_many': [vp, i32, i32, vp],
     'arx_mw_prep': [vp, vp, f32, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp],
+    'arx_score_max': [vp, vp, i64, i64, vp, vp],
+    'arx_token_pool_fwd': [vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp],
+    'arx_token_pool_bwd': [vp, vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp, vp],
+    'arx_rowsum': [vp, i64, i64, vp, i32, vp],
     'arx_gather_pairs': [vp, vp, vp, i64, vp, vp, vp],
     'arx_cbow_window_batch': [vp, vp, vp, vp, i64, i64, i64, i32, i32, i32, vp, vp, vp, vp, vp],
     'arx_lstm_pad_batch': [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
@@ -106,6 +111,7 @@ SIGNATURES = {
 _ERR = {-1: 'ARX_E_BADARG', -2: 'ARX_E_LAUNCH', -3: 'ARX_E_UNSUPPORTED', -4: 'ARX_E_CAPACITY'}
 
 _lib = None
+TUNING = {}        # arx_set_tuning settings taken from ARX_TUNE at load time (the plan capacity follows 'heavy')
 launch_count = 0   # number of C-ABI compute calls issued (bench.py's gpu_launches evidence)
 
 
@@ -131,6 +137,7 @@ def load():
         k, v = kv.split('=')
         if lib.arx_set_tuning(k.encode(), int(v)) != 0:
             raise RuntimeError('ARX_TUNE: bad setting %r' % kv)
+        TUNING[k] = int(v)
     return lib
 
 

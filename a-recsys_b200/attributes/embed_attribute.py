@@ -95,7 +95,8 @@ class _Plan(object):
 
     def __init__(self, device, cap_rows, cap_occ, dim):
         i32 = dict(dtype=torch.int32, device=device)
-        cap_chunks = cap_occ // 32 + 1
+        _lib.load()
+        cap_chunks = 2 * cap_occ // _lib.TUNING.get('heavy', _lib.HEAVY_DEFAULT) + 1     # rows above `heavy` entries: < 2 c / heavy chunks each
         self.chunk_row = torch.empty(cap_chunks, **i32)
         self.row_chunk0 = torch.empty(cap_rows, **i32)
         self.row_done = torch.zeros(cap_rows, **i32)
@@ -191,6 +192,7 @@ class EmbeddingAttribute(object):
             self.item2logit_dev = torch.from_numpy(i2l).to(self.device)
         self.sampled_ids = None
         self.sampled_pos_dev = None
+        self.dense_table_grads = {}     # prefix -> {variable name: dense gradient}  (output_feat 2 / 3 scoring)
         self.pos_csr = {}          # (kind) -> (ptr, idx) per-user positives, device
         self.pos_item_set = None
         self.pos_item_set_eval = None
@@ -392,19 +394,113 @@ class EmbeddingAttribute(object):
     # -- embed_attribute.py:148-206 --------------------------------------------------------
     def get_prediction(self, latent, pool='full', device='/gpu:0', output_feat=1):
         """logits [mb, V] (or [mb, S]).  output_feat 0 (id only) and 1 (mean pooling) are linear
-        in the tables and use the pool-first form; 2/3 (max / log-sum-exp pooling) are not
-        implemented on the CUDA path yet."""
-        if output_feat not in (0, 1):
+        in the tables and use the pool-first form; 2 / 3 (max / log-sum-exp pooling of the token scores) are not, and
+        take the reference's literal order (token_prediction)."""
+        if output_feat not in (0, 1, 2, 3):
             print('Error: Attribute combination not implemented!')
             exit(1)
         if isinstance(latent, list):
             raise NotImplementedError('per-attribute latent lists are not supported on the CUDA path')
+        if output_feat in (2, 3):
+            return self.token_prediction(latent, pool, output_feat)
         P, beta, ids = self.pool_catalog(pool, output_feat)
         mb, N = latent.shape[0], P.shape[0]
         logits = torch.empty((mb, N), dtype=torch.float32, device=self.device)
         _lib.gemm(latent, P, logits, mb, N, self.dim, 0, 1, beta)
         self._last_pred = (latent, P, beta, ids, pool, output_feat)
         return logits
+
+    # -- embed_attribute.py:163-205 for output_feat 2 / 3 ------------------------------------------------
+    def _catalog_csr(self, pool):
+        """Per attribute, the catalog in logit (or pool) order as (token ids, ptr): the `full_*_tr` / sampled constants
+        of the reference (:97-108, :320-348) in CSR form, built once per catalog / pool refresh."""
+        key = ('csr', pool, getattr(self, '_sampled_version', 0) if pool != 'full' else 0)
+        cache = getattr(self, '_csr_cache', {})
+        if key in cache:
+            return cache[key]
+        ids = (self.catalog_ids if pool == 'full' else self.sampled_ids).long()
+        feats_cat, feats_mul, starts, lengths = self.att['item'][:4]
+        cats = [fc[ids].contiguous() for fc in feats_cat]
+        muls = []
+        for f in range(len(feats_mul)):
+            l = lengths[f][ids].long()
+            st = starts[f][ids].long()
+            ptr_ = torch.zeros(ids.numel() + 1, dtype=torch.int64, device=self.device)
+            ptr_[1:] = torch.cumsum(l, 0)
+            seg = torch.repeat_interleave(torch.arange(ids.numel(), device=self.device), l)
+            pos = torch.arange(int(ptr_[-1].item()), device=self.device) - ptr_[:-1][seg] + st[seg]
+            muls.append((feats_mul[f][pos].contiguous(), ptr_))
+        self._csr_cache = {k: v for k, v in cache.items() if k[1] != pool}
+        self._csr_cache[key] = (cats, muls)
+        return cats, muls
+
+    def token_prediction(self, latent, pool='full', output_feat=2):
+        """logits [n, V] in the reference's literal order: per attribute f the token scores s_f = E_f latent^T + beta_f
+        ([V_f, n], one contraction), pooled per catalog item by segment max (2) or m + log(1 + sum exp(s - m)) (3), a
+        categorical attribute contributing the score of its single token; mean over attributes (:205).  Keeps what
+        token_prediction_backward needs in self._last_tokpred."""
+        assert self.shard is None, 'output_feat 2 / 3 is not provided for row-sharded tables'
+        pre = self._out_prefix()
+        ts = self.sets[pre]
+        n = latent.shape[0]
+        V = (self.catalog_ids if pool == 'full' else self.sampled_ids).numel()
+        cats, muls = self._catalog_csr(pool)
+        F = ts.n_attr
+        out_vm = torch.zeros((V, n), dtype=torch.float32, device=self.device)
+        lat = latent.contiguous()
+        saved = []
+        for k in range(F):
+            E, b = self.params[ts.names[k]], self.params[ts.bias_names[k]].reshape(-1)
+            Vf = E.shape[0]
+            S = torch.empty((Vf, n), dtype=torch.float32, device=self.device)
+            _lib.gemm(E, lat, S, Vf, n, self.dim, 0, 1)
+            if k < ts.n_cat:
+                vals, ptr_, mode = cats[k], None, 1
+            else:
+                (vals, ptr_), mode = muls[k - ts.n_cat], output_feat
+            arg = torch.empty((V, n), dtype=torch.int32, device=self.device) if mode == 2 else None
+            den = torch.empty((V, n), dtype=torch.float32, device=self.device) if mode == 3 else None
+            pk = None
+            if mode == 3:
+                pk = torch.zeros(1, dtype=torch.int64, device=self.device)
+                call('arx_score_max', S.data_ptr(), b.data_ptr(), Vf, n, pk.data_ptr())
+            call('arx_token_pool_fwd', S.data_ptr(), b.data_ptr(), n, vals.data_ptr(), ptr(ptr_), V, mode, ptr(pk), 1.0 / F,
+                 out_vm.data_ptr(), ptr(arg), ptr(den))
+            saved.append((k, S, vals, ptr_, mode, pk, arg, den))
+        logits = torch.empty((n, V), dtype=torch.float32, device=self.device)
+        call('arx_transpose', out_vm.data_ptr(), V, n, logits.data_ptr(), 0)
+        self._last_tokpred = (lat, saved, V, pool, output_feat)
+        self._last_pred = (latent, None, None, self.catalog_ids if pool == 'full' else self.sampled_ids, pool, output_feat)
+        return logits
+
+    def token_prediction_backward(self, dlogits):
+        """Adjoint of token_prediction for d(loss)/d(logits) [n, V]: returns d(latent) [n, dim] and ACCUMULATES the dense
+        gradients of the output tables and biases (every token row scores every batch row) into self.dense_table_grads —
+        applied, merged with any sparse look-up gradients of the same tables, by apply_gradients."""
+        lat, saved, V, pool, output_feat = self._last_tokpred
+        pre = self._out_prefix()
+        ts = self.sets[pre]
+        n, F = lat.shape[0], ts.n_attr
+        d_vm = torch.empty((V, n), dtype=torch.float32, device=self.device)
+        call('arx_transpose', dlogits.data_ptr(), n, V, d_vm.data_ptr(), 0)
+        dlat = torch.zeros((n, self.dim), dtype=torch.float32, device=self.device)
+        grads = self.dense_table_grads.setdefault(pre, {})
+        scratch = torch.zeros(1, dtype=torch.float32, device=self.device)
+        for (k, S, vals, ptr_, mode, pk, arg, den) in saved:
+            E, b = self.params[ts.names[k]], self.params[ts.bias_names[k]].reshape(-1)
+            Vf = E.shape[0]
+            dS = torch.zeros((Vf, n), dtype=torch.float32, device=self.device)
+            call('arx_token_pool_bwd', d_vm.data_ptr(), S.data_ptr(), b.data_ptr(), n, vals.data_ptr(), ptr(ptr_), V, mode,
+                 ptr(pk), 1.0 / F, ptr(arg), ptr(den), dS.data_ptr(), scratch.data_ptr())
+            name, bname = ts.names[k], ts.bias_names[k]
+            first = name not in grads
+            if first:
+                grads[name] = torch.empty_like(E)
+                grads[bname] = torch.empty((Vf,), dtype=torch.float32, device=self.device)
+            _lib.gemm(dS, lat, grads[name], Vf, self.dim, n, 0, 0, None, 1.0, 0.0 if first else 1.0)      # dE_f (+)= dS latent
+            call('arx_rowsum', dS.data_ptr(), Vf, n, grads[bname].data_ptr(), 0 if first else 1)
+            _lib.gemm(dS, E, dlat, n, self.dim, Vf, 1, 0, None, 1.0, 1.0)                                  # d latent += dS^T E_f
+        return dlat
 
     def fused_ce(self, latent, targets, row_scale=None, want_grad=True, pool='full', output_feat=1):
         """get_prediction (:148-206) + compute_loss(..., 'ce') (:530) + their gradients without ever writing
@@ -763,11 +859,34 @@ class EmbeddingAttribute(object):
             n += t.shape[0]
         return base if n == base.shape[0] else base[:n]
 
+    def _merge_dense(self):
+        """Tables that hold a dense gradient (token_prediction_backward) AND pending look-up gradients get ONE summed dense
+        gradient, as TensorFlow sums a variable's IndexedSlices and dense gradients before the norm and the update."""
+        for prefix, grads in self.dense_table_grads.items():
+            ts = self.sets[prefix]
+            if grads and ts.pending:
+                rows = self.row_gradients(prefix)                 # densified look-up gradients; clears ts.pending
+                for name, g in rows.items():
+                    if name in grads:
+                        grads[name] += g.reshape(grads[name].shape)
+
+    def apply_dense_table_grads(self, lr, opt=OPT_ADAGRAD, grad_scale=None):
+        for prefix, grads in self.dense_table_grads.items():
+            for name, g in grads.items():
+                w, acc = self.params[name], self.accs[name]
+                call('arx_dense_update', w.data_ptr(), acc.data_ptr(), g.contiguous().data_ptr(), w.numel(), float(lr),
+                     ptr(grad_scale), opt)
+        self.dense_table_grads = {}
+
     def sparse_sumsq(self, out, dense_semantics=()):
         """Add the table-gradient terms of clip_by_global_norm into out[0].  Table sets named in
         `dense_semantics` also feed the scoring matmul, so TF holds their gradient as ONE dense
         tensor (duplicates merged before the norm); the others are IndexedSlices (norm over the
         un-merged slices)."""
+        self._merge_dense()
+        for grads in self.dense_table_grads.values():
+            for g in grads.values():
+                out += (g * g).sum()
         for ts in self.sets.values():
             if not ts.pending:
                 continue
@@ -799,6 +918,9 @@ class EmbeddingAttribute(object):
         # The table sets are independent and each of their kernels is latency-bound on its own
         # (random 512-byte rows, L2 atomics): run them on parallel streams (parallel branches of the
         # captured CUDA graph) so that their memory traffic overlaps.
+        if self.dense_table_grads:
+            self._merge_dense()
+            self.apply_dense_table_grads(lr, opt, grad_scale)
         main = torch.cuda.current_stream()
         busy = [ts for ts in self.sets.values() if ts.pending]
         if (busy and self.dim % 4 == 0 and opt in (OPT_ADAGRAD, OPT_SGD)

@@ -12,7 +12,8 @@ namespace {
 
 constexpr int kMaxAttr = 32;          // one lane per attribute for the (start,len) prefetch
 constexpr int kRowsInFlight = 8;      // independent row loads per lane group
-constexpr int kHeavy = 64;            // bucket size above which a row is split across warps
+constexpr int kHeavyMax = 64;         // largest bucket a single warp reduces; larger ones are split into chunks of `heavy`
+                                      // entries (arx_set_tuning("heavy", 8..64)) that different warps reduce
 
 // ---- tiny vector abstraction: VEC = 4 (float4, dim % 4 == 0) or 1 (any dim) --------
 template <int VEC> struct V;
@@ -474,7 +475,7 @@ plan_count_kernel(const arx_attr_desc* __restrict__ g_attrs, int attr_begin, int
   }
 }
 
-__global__ void plan_alloc_kernel(const arx_attr_desc* __restrict__ g_attrs, arx_bwd_plan plan) {
+__global__ void plan_alloc_kernel(const arx_attr_desc* __restrict__ g_attrs, arx_bwd_plan plan, int kHeavy) {
   const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
   const int lane = threadIdx.x & 31;
   for (int u0 = blockIdx.x * blockDim.x + threadIdx.x - lane; u0 < nu; u0 += gridDim.x * blockDim.x) {
@@ -803,13 +804,15 @@ __device__ __forceinline__ void row_update(const arx_attr_desc& a, size_t off, t
 
 constexpr int kRowsPerStep = 4;
 
-template <int VEC>
+constexpr int kFlatExtra = 128;       // extra bucket entries (beyond the first of each row) a warp pre-loads per 32 rows
+
+template <int VEC, bool FLAT>
 __device__ __forceinline__ void
 pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
                     const arx_bwd_plan& plan, const float* __restrict__ dout, long long dout_stride,
                     const float* __restrict__ dbias, float lr,
                     const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
-                    float* __restrict__ bias_rows_out) {
+                    float* __restrict__ bias_rows_out, int kHeavy) {
   using VT = typename V<VEC>::T;
   if (plan.counters[2] != 0) return;
   const int lane = threadIdx.x & 31;
@@ -901,6 +904,42 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
     const bool row_bias = light && dbias != nullptr && s_attrs[f].bias != nullptr;
     float gb_mine = row_bias ? w0 * __ldg(dbias + src0) : 0.f;
     const unsigned lightmask = __ballot_sync(ARX_FULL_MASK, light);
+    // FLAT: the bucket entries beyond the first of the warp's 32 rows form (up to the gaps of hot rows) one contiguous
+    // run of the bucket arrays.  All of them are fetched here in one round of independent, mostly coalesced loads
+    // (entry i of the run sits in lane i & 31, slot i >> 5), so that the row steps below never wait on a
+    // bucket_src -> gradient-row chain: rows with several contributions (the item side: 2.7 per row) cost one extra
+    // wave of gradient loads instead of two dependent round trips per row, one row after the other.
+    const int extra = light ? cnt - 1 : 0;
+    int incl = extra;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(ARX_FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int excl = incl - extra;
+    const int n_extra = __shfl_sync(ARX_FULL_MASK, incl, 31);
+    const bool flat = FLAT && n_extra <= kFlatExtra;
+    int es[kFlatExtra / 32]; float ew[kFlatExtra / 32], eb[kFlatExtra / 32];
+    if (flat) {
+#pragma unroll
+      for (int j = 0; j < kFlatExtra / 32; ++j) {
+        const int i = lane + 32 * j;
+        int lo = 0;                                   // row (lane) that owns entry i: first lane with incl > i
+#pragma unroll
+        for (int st = 16; st > 0; st >>= 1) {
+          const int t = __shfl_sync(ARX_FULL_MASK, incl, lo + st - 1);
+          if (t <= i) lo += st;
+        }
+        const int rb = __shfl_sync(ARX_FULL_MASK, base, lo), rx = __shfl_sync(ARX_FULL_MASK, excl, lo);
+        const int hasb = __shfl_sync(ARX_FULL_MASK, (int)row_bias, lo);
+        es[j] = 0; ew[j] = 0.f; eb[j] = 0.f;
+        if (i < n_extra) {
+          es[j] = __ldg(plan.bucket_src + rb + 1 + (i - rx));
+          ew[j] = __ldg(plan.bucket_w + rb + 1 + (i - rx));
+          if (hasb) eb[j] = ew[j] * __ldg(dbias + es[j]);
+        }
+      }
+    }
     for (int c0 = 0; c0 < nvec; c0 += 32) {
       const int col = c0 + lane;
       const bool colok = col < nvec;
@@ -927,6 +966,40 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
           g[q] = ok ? V<VEC>::mul(V<VEC>::ldg(dout + (size_t)s0 * dout_stride + (size_t)col * VEC), wq)
                     : V<VEC>::zero();
         }
+        if (flat) {
+          int ie[kRowsPerStep];                       // running ends of the rows' extra entries inside the run
+#pragma unroll
+          for (int q = 0; q < kRowsPerStep; ++q) ie[q] = __shfl_sync(ARX_FULL_MASK, incl, r + q);
+          const int i_end = ie[kRowsPerStep - 1];
+          for (int i0 = __shfl_sync(ARX_FULL_MASK, excl, r); i0 < i_end; i0 += kRowsInFlight) {
+            VT v[kRowsInFlight]; float wk[kRowsInFlight]; int qk[kRowsInFlight];
+#pragma unroll
+            for (int k = 0; k < kRowsInFlight; ++k) {
+              const int i = i0 + k;
+              const bool ok = i < i_end;
+              const int j = i >> 5;                   // warp-uniform slot
+              const int sj = j == 0 ? es[0] : (j == 1 ? es[1] : (j == 2 ? es[2] : es[3]));
+              const float wj = j == 0 ? ew[0] : (j == 1 ? ew[1] : (j == 2 ? ew[2] : ew[3]));
+              const int sk = __shfl_sync(ARX_FULL_MASK, sj, i & 31);
+              wk[k] = ok ? __shfl_sync(ARX_FULL_MASK, wj, i & 31) : 0.f;
+              qk[k] = 0;
+#pragma unroll
+              for (int q = 0; q < kRowsPerStep - 1; ++q) qk[k] += (i >= ie[q]) ? 1 : 0;
+              v[k] = (ok && colok) ? V<VEC>::ldg(dout + (size_t)sk * dout_stride + (size_t)col * VEC) : V<VEC>::zero();
+              if (c0 == 0 && dbias != nullptr) {
+                const float bj = j == 0 ? eb[0] : (j == 1 ? eb[1] : (j == 2 ? eb[2] : eb[3]));
+                const float bt = __shfl_sync(ARX_FULL_MASK, bj, i & 31);
+                if (ok && lane == r + qk[k]) gb_mine += bt;
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kRowsInFlight; ++k) {
+#pragma unroll
+              for (int q = 0; q < kRowsPerStep; ++q)          // arithmetic select: keeps g[] in registers
+                V<VEC>::fma(g[q], qk[k] == q ? wk[k] : 0.f, v[k]);
+            }
+          }
+        } else {
 #pragma unroll
         for (int q = 0; q < kRowsPerStep; ++q) {
           if (cq[q] > 1) {                           // warp-uniform: remaining bucket entries
@@ -936,6 +1009,7 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
                                                  wb ? dbias : nullptr, gbx));
             if (lane == r + q) gb_mine += gbx;
           }
+        }
         }
 #pragma unroll
         for (int q = 0; q < kRowsPerStep; ++q) {
@@ -962,16 +1036,16 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
   }
 }
 
-template <int VEC>
+template <int VEC, bool FLAT>
 __global__ void __launch_bounds__(256, 2)
 pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
                        arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
                        const float* __restrict__ dbias, float lr,
                        const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
-                       float* __restrict__ bias_rows_out) {
+                       float* __restrict__ bias_rows_out, int heavy) {
   __shared__ arx_attr_desc s_attrs[kMaxAttr];
   stage_descs(s_attrs, g_attrs, n_attr);
-  pool_bwd_apply_body<VEC>(s_attrs, dim, plan, dout, dout_stride, dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+  pool_bwd_apply_body<VEC, FLAT>(s_attrs, dim, plan, dout, dout_stride, dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, heavy);
 }
 
 // Several table sets (the user and the item tables of one training step) in ONE launch: a warp that has run out of rows
@@ -989,7 +1063,7 @@ struct ApplyManyParams {
   ApplySet set[kApplySets];
   const float* grad_scale;
   float lr;
-  int n_sets, dim, opt;
+  int n_sets, dim, opt, heavy;
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -1006,11 +1080,11 @@ pool_bwd_apply_many_kernel(const ApplyManyParams mp) {
   __syncthreads();
   // constant indices into the parameter block: a run-time index would make the compiler copy the parameters to local
   // memory and read every plan pointer through it inside the inner loops
-  pool_bwd_apply_body<4>(s_attrs_all[0], mp.dim, mp.set[0].plan, mp.set[0].dout, mp.set[0].dout_stride, mp.set[0].dbias,
-                         mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr);
+  pool_bwd_apply_body<4, false>(s_attrs_all[0], mp.dim, mp.set[0].plan, mp.set[0].dout, mp.set[0].dout_stride, mp.set[0].dbias,
+                         mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr, mp.heavy);
   if (mp.n_sets > 1)
-    pool_bwd_apply_body<4>(s_attrs_all[1], mp.dim, mp.set[1].plan, mp.set[1].dout, mp.set[1].dout_stride, mp.set[1].dbias,
-                           mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr);
+    pool_bwd_apply_body<4, false>(s_attrs_all[1], mp.dim, mp.set[1].plan, mp.set[1].dout, mp.set[1].dout_stride, mp.set[1].dbias,
+                           mp.lr, mp.grad_scale, mp.opt, nullptr, nullptr, mp.heavy);
 }
 
 // IndexedSlices part of the global norm: sum over occurrences of w^2 * ||dOut[src]||^2
@@ -1073,6 +1147,9 @@ rows_sumsq_kernel(const float* __restrict__ rows, const float* __restrict__ brow
 
 int g_tune_flat_epb = 0;         // arx_set_tuning("flat_epb", 0 = auto | 1..16): entities per CTA of the flat forward
 int g_tune_apply_cps = 4;        // arx_set_tuning("apply_ctas_per_sm", 1..4)
+int g_tune_heavy = 64;          // arx_set_tuning("heavy", 8..64): bucket size above which a row is split across warps; must not change
+                                // between building a plan and applying it; arx_bwd_plan.cap_chunks >= 2 * cap_occ / heavy + 1
+int g_tune_apply_flat = 1;      // arx_set_tuning("apply_flat", 0 | 1): pre-loaded flat bucket entries in the row phase of the apply kernel
 int g_tune_plan_agg = 3;         // arx_set_tuning("plan_agg", 0 | 1): block-aggregated plan_count / plan_fill (tables < 2^27 rows)
 
 inline int pick_grid(long long warps_needed, int threads) {
@@ -1248,7 +1325,7 @@ extern "C" int arx_bwd_plan_count(const arx_attr_desc* attrs, int attr_begin, in
 
 extern "C" int arx_bwd_plan_alloc(const arx_attr_desc* attrs, arx_bwd_plan plan, void* stream) {
   if (!attrs || !plan_args_ok(plan)) return ARX_E_BADARG;
-  plan_alloc_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(attrs, plan);
+  plan_alloc_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(attrs, plan, g_tune_heavy);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }
@@ -1300,12 +1377,15 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = arx_num_sms() * g_tune_apply_cps;   // persistent (2 CTAs/SM): warps stride over the device-side row list
   const bool v4 = (dim % 4 == 0) && (dout_stride % 4 == 0) && (((uintptr_t)dout & 15) == 0);
-  if (v4)
-    pool_bwd_apply_kernel<4><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                    dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+  if (v4 && g_tune_apply_flat)
+    pool_bwd_apply_kernel<4, true><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+                                                          dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
+  else if (v4)
+    pool_bwd_apply_kernel<4, false><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
   else
-    pool_bwd_apply_kernel<1><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                    dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out);
+    pool_bwd_apply_kernel<1, false><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
+                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }
@@ -1325,7 +1405,7 @@ extern "C" int arx_pool_bwd_apply_many(const arx_apply_set* sets, int n_sets, in
     mp.set[i].attrs = q.attrs; mp.set[i].dout = q.dout; mp.set[i].dbias = q.dbias;
     mp.set[i].dout_stride = q.dout_stride; mp.set[i].plan = q.plan; mp.set[i].n_attr = q.n_attr;
   }
-  mp.grad_scale = grad_scale_dev; mp.lr = lr; mp.n_sets = n_sets; mp.dim = dim; mp.opt = opt;
+  mp.grad_scale = grad_scale_dev; mp.lr = lr; mp.n_sets = n_sets; mp.dim = dim; mp.opt = opt; mp.heavy = g_tune_heavy;
   const int grid = arx_num_sms() * g_tune_apply_cps;   // persistent: warps stride over the device-side row lists
   pool_bwd_apply_many_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(mp);
   ARX_CHECK_LAUNCH();
@@ -1343,6 +1423,15 @@ extern "C" int arx_set_tuning(const char* key, int value) {
   }
   if (eq("plan_agg")) {
     g_tune_plan_agg = value & 3;          // bit 0: count, bit 1: fill
+    return ARX_OK;
+  }
+  if (eq("heavy")) {
+    if (value < 8 || value > kHeavyMax) return ARX_E_BADARG;
+    g_tune_heavy = value;
+    return ARX_OK;
+  }
+  if (eq("apply_flat")) {
+    g_tune_apply_flat = value & 1;
     return ARX_OK;
   }
   if (eq("apply_ctas_per_sm")) {

@@ -221,7 +221,8 @@ class SeqModel(object):
             eff = 'warp'                                                      # losses_full (:311,:510)
         pre = m._out_prefix()
         pool = 'sampled' if eff == 'mw' else 'full'
-        fused = m.fused_ce(Hf, tgt, row_scale, train, pool, self.output_feat) if eff == 'ce' else None
+        nonlinear = self.output_feat in (2, 3)      # max / log-sum-exp pooling of the token scores: literal order (K3m)
+        fused = m.fused_ce(Hf, tgt, row_scale, train, pool, self.output_feat) if (eff == 'ce' and not nonlinear) else None
         if fused is not None:
             # all T*mb positions scored against the catalog and reduced to the softmax CE on the tensor
             # cores without materialising [T*mb, V] logits (seqModel.py:480-493 + sequence_loss)
@@ -232,8 +233,12 @@ class SeqModel(object):
                 return float(total.item()) if sync else total
             dH, dP, dbeta = grads
             return self._finish_step(m, pre, cids, dP, dbeta, dH, ictx, users, item_ids, T, mb, total, sync)
-        P, beta, cids = m.pool_catalog(pool, self.output_feat)
-        N = P.shape[0]
+        if nonlinear:
+            P = beta = cids = None
+            N = (m.catalog_ids if pool == 'full' else m.sampled_ids).numel()
+        else:
+            P, beta, cids = m.pool_catalog(pool, self.output_feat)
+            N = P.shape[0]
         users_rep = users.repeat(T) if eff != 'ce' else None
         tscore = dts_all = Pt = None
         if eff == 'mw':
@@ -241,21 +246,35 @@ class SeqModel(object):
             Pt = m._last_target[1]
             dts_all = torch.empty((T * mb,), dtype=torch.float32, device=dev)
         total = torch.zeros((), dtype=torch.float32, device=dev)
+        dP = dbeta = None
         if train:
             dH = torch.empty_like(Hf)
-            dP = torch.zeros_like(P)
-            dbeta = torch.zeros((N,), dtype=torch.float32, device=dev)
+            if not nonlinear:
+                dP = torch.zeros_like(P)
+                dbeta = torch.zeros((N,), dtype=torch.float32, device=dev)
         rows_per_chunk = max(mb, int(self.max_score_bytes // (4 * N)) // mb * mb)
+        if nonlinear:
+            # the reference scores one time step per get_prediction call (seqModel.py:480-493), and the log-sum-exp
+            # pooling is anchored at the maximum of THAT call's token scores (embed_attribute.py:197): log(e^m + sum e^s)
+            # depends on m, so the calls must not be merged
+            rows_per_chunk = mb
         for r0 in range(0, T * mb, rows_per_chunk):
             r1 = min(T * mb, r0 + rows_per_chunk)
             n = r1 - r0
-            S = torch.empty((n, N), dtype=torch.float32, device=dev)
-            _lib.gemm(Hf[r0:r1], P, S, n, N, self.size, 0, 1, beta)
+            if nonlinear:
+                S = m.get_prediction(Hf[r0:r1], pool, output_feat=self.output_feat)
+            else:
+                S = torch.empty((n, N), dtype=torch.float32, device=dev)
+                _lib.gemm(Hf[r0:r1], P, S, n, N, self.size, 0, 1, beta)
             bl = m.compute_loss(S, tscore[r0:r1] if eff == 'mw' else tgt[r0:r1], eff,
                                 row_scale=row_scale[r0:r1], want_grad=train, forward_only=forward_only,
                                 pos_rows=users_rep[r0:r1].contiguous() if users_rep is not None else None)
             total += (bl * row_scale[r0:r1]).sum()
-            if train:
+            if train and nonlinear:
+                dH[r0:r1] = m.token_prediction_backward(S)         # table / bias gradients accumulate in m.dense_table_grads
+                if eff == 'mw':
+                    dts_all[r0:r1] = m._last_dtarget
+            elif train:
                 _lib.gemm(S, P, dH[r0:r1], n, self.size, N, 0, 0)
                 dPc = torch.empty_like(P)
                 _lib.gemm(S, Hf[r0:r1], dPc, N, self.size, n, 1, 0)
@@ -280,8 +299,9 @@ class SeqModel(object):
         """Backward through the catalog pooling, the LSTM and the input embeddings, then the clipped
         optimizer step (seqModel.py:173-182)."""
         dev = self.device
-        rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
-        m.push_grad(pre, rng_out, cids, POOL_MEAN, dP, dbeta, plan_key=None)
+        if dP is not None:
+            rng_out = m.sets[pre].attr_range(no_attribute=(self.output_feat == 0))
+            m.push_grad(pre, rng_out, cids, POOL_MEAN, dP, dbeta, plan_key=None)
         dX = self.cell.backward(dH.view(T, mb, self.size))
         self._inputs_backward(ictx, dX, users, item_ids, T, mb)
 
@@ -316,10 +336,19 @@ class SeqModel(object):
         Hout = self.cell.forward(X, 1.0)
         pos = torch.as_tensor(np.asarray(positions, dtype=np.int64)).to(self.device)
         hsel = Hout[pos, torch.arange(mb, device=self.device)].contiguous()            # [mb, H]
-        P, beta, _ = m.pool_catalog('full', self.output_feat)
-        N = P.shape[0]
-        S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
-        _lib.gemm(hsel, P, S, mb, N, self.size, 0, 1, beta)
+        if self.output_feat in (2, 3):
+            # one get_prediction per time step, as the reference's graph has it (the output_feat 3 pooling depends on
+            # the maximum token score of the step's whole batch); every sequence keeps the row of its last position
+            N = m.catalog_ids.numel()
+            S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
+            for t in sorted(set(int(p) for p in positions)):
+                sel = (pos == t).nonzero().reshape(-1)
+                S[sel] = m.get_prediction(Hout[t].contiguous(), 'full', output_feat=self.output_feat)[sel]
+        else:
+            P, beta, _ = m.pool_catalog('full', self.output_feat)
+            N = P.shape[0]
+            S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
+            _lib.gemm(hsel, P, S, mb, N, self.size, 0, 1, beta)
         idx = torch.empty((mb, self.topk_n), dtype=torch.int32, device=self.device)
         val = torch.empty((mb, self.topk_n), dtype=torch.float32, device=self.device)
         call('arx_topk_rows', S.data_ptr(), mb, N, S.stride(0), self.topk_n, idx.data_ptr(), val.data_ptr())

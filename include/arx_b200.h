@@ -376,6 +376,22 @@ int arx_lstm_pad_batch(const int64_t* seq_ptr, const int32_t* seq_items, const i
                        int32_t* out_inputs, int32_t* out_targets, float* out_weights, void* stream);
 int arx_gumbel_keys(const float* logp, int64_t n, uint64_t* rng_state, float* keys, void* stream);
 
+/* K3m — non-linear attribute pooling of the catalog scores (attributes/embed_attribute.py:194-200, output_feat 2 / 3).
+ * S [Vf, mb]: token scores E_f u^T (token-major as the reference's `innerp`), bias [Vf] or NULL; the catalog CSR of the
+ * attribute: values (token ids in catalog order) + ptr [V+1] (NULL: one token per item, i.e. a categorical attribute).
+ * mode 1 = gather / sum (:172), 2 = segment max (:195), 3 = m + log(1 + sum exp(s - m)) with m the maximum of the WHOLE
+ * score matrix (:197-199; arx_score_max computes it, packed with its position).  out [V, mb] += scale * pooled.
+ * The adjoint adds scale * dOut through the pooling into dS [Vf, mb] (atomics; for mode 3 also the gradient that reaches
+ * the global maximum).  arx_rowsum: out[r] (+)= sum_c X[r, c]  (bias gradients of token-major score gradients). */
+int arx_score_max(const float* S, const float* bias, int64_t Vf, int64_t mb, uint64_t* packed, void* stream);
+int arx_token_pool_fwd(const float* S, const float* bias, int64_t mb, const int32_t* values, const int64_t* ptr, int64_t V,
+                       int mode, const uint64_t* packed_max, float scale, float* out, int32_t* argmax, float* denom,
+                       void* stream);
+int arx_token_pool_bwd(const float* dOut, const float* S, const float* bias, int64_t mb, const int32_t* values,
+                       const int64_t* ptr, int64_t V, int mode, const uint64_t* packed_max, float scale,
+                       const int32_t* argmax, const float* denom, float* dS, float* dmax_scratch, void* stream);
+int arx_rowsum(const float* X, int64_t rows, int64_t cols, float* out, int accumulate, void* stream);
+
 /* K10 — tf.nn.top_k(sorted=True) over materialised scores (hmf/hmf_model.py:154):
  * descending, ties -> lower index. idx_out [mb,k] int32, val_out [mb,k] or NULL. */
 int arx_topk_rows(const float* scores, int64_t mb, int64_t V, int64_t ld, int k,

@@ -285,7 +285,17 @@ class TorchRefSeq(TorchRefHMF):
             innerps.append(innerp.index_select(0, cat[i]))
         for i in range(n2):
             innerp = self.p['%sembed_mulhot_%d' % (pre, i)] @ u.t() + self.p['%s_bias_mulhot_%d' % (pre, i)]
-            innerps.append(seg_sum(innerp.index_select(0, val[i]), seg[i], V) / leng[i])
+            if self.output_feat in (0, 1):
+                innerps.append(seg_sum(innerp.index_select(0, val[i]), seg[i], V) / leng[i])       # :192
+            elif self.output_feat == 2:                                                            # :195 segment_max
+                rows = innerp.index_select(0, val[i])
+                idx = seg[i].reshape(-1, 1).expand_as(rows)
+                out = torch.full((V, rows.shape[1]), float('-inf'), dtype=rows.dtype)
+                innerps.append(out.scatter_reduce(0, idx, rows, 'amax', include_self=True))
+            else:                                                                                  # :197-199
+                score_max = innerp.max()
+                innerps.append(score_max + torch.log(1 + seg_sum(torch.exp(innerp - score_max).index_select(0, val[i]),
+                                                                 seg[i], V)))
         return torch.stack(innerps, 0).mean(0).t()
 
     def _tscore(self, u, inds):

@@ -260,6 +260,10 @@ LSTMX_CASES = {
     'warp_noitemfeat': ('warp', False, False, True, 0.5, 5.0, {'no_input_item_feature': True}),
     # MultiRNNCell([DropoutWrapper(LSTMCell, in)] * 2) + DropoutWrapper(out) (seqModel.py:99-103)
     'ce_2layers': ('ce', False, False, True, 0.5, 5.0, {'num_layers': 2}),
+    # non-linear attribute pooling of the token scores (embed_attribute.py:194-200): segment max / log-sum-exp
+    'ce_outfeat2': ('ce', False, False, True, 0.5, 5.0, {'output_feat': 2}),
+    'ce_outfeat3_sep': ('ce', False, True, True, 0.5, 5.0, {'output_feat': 3}),
+    'warp_outfeat2_sep': ('warp', True, True, True, 0.5, 5.0, {'output_feat': 2}),
 }
 
 

@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libarx_b200.so')
+LIB_PATH = os.environ.get('ARX_LIB') or os.path.join(_HERE, 'lib', 'libarx_b200.so')     # ARX_LIB: A/B of build variants
 
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 c_f32p = ctypes.POINTER(ctypes.c_float)

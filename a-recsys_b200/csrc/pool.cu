@@ -812,8 +812,9 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
                     const arx_bwd_plan& plan, const float* __restrict__ dout, long long dout_stride,
                     const float* __restrict__ dbias, float lr,
                     const float* __restrict__ grad_scale_dev, int opt, float* __restrict__ rows_out,
-                    float* __restrict__ bias_rows_out, int kHeavy) {
+                    float* __restrict__ bias_rows_out, int kHeavyArg) {
   using VT = typename V<VEC>::T;
+  const int kHeavy = kHeavyArg & 0xff;
   if (plan.counters[2] != 0) return;
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -825,8 +826,10 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
   float* __restrict__ part = plan.partials;
   float* __restrict__ part_b = plan.partials + (size_t)plan.cap_chunks * dim;
 
+  // measurement only (arx_set_tuning("apply_phases", 1 | 2 | 3)): bits 8-9 of the argument switch a phase off
+  const int phase_off = (kHeavyArg >> 8) & 3;
   // ---- phase 1: chunks of the hot rows (longest work first) ---------------------------
-  for (long long ch = warp0; ch < nchunks; ch += nwarps) {
+  for (long long ch = warp0; ch < ((phase_off & 1) ? 0 : nchunks); ch += nwarps) {
     const int u = plan.chunk_row[ch];
     const int cb = plan.row_chunk0[u];
     const int k = (int)ch - cb;
@@ -888,8 +891,14 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
   }
 
   // ---- phase 2: all other rows, 32 per warp iteration -----------------------------------
-  for (long long u0 = warp0 * 32; u0 < nu; u0 += nwarps * 32) {
-    const int u = (int)u0 + lane;
+  // Rows are dealt to the warps STRIDED: lane l of warp-iteration `it` takes row l * n_iter + it, so neighbours in the
+  // unique list (first-touch order: the ~100 rows of one popular entity, each with as many contributions as the entity
+  // has occurrences in the batch) land in ~100 different warps instead of filling three warps with 30 x the average
+  // work — those few warps used to set the duration of the item-side launch (Zipf item popularity).
+  const int n_iter = (nu + 31) >> 5;
+  const bool strided = ((kHeavyArg >> 10) & 1) == 0;
+  for (long long it = warp0; it < ((phase_off & 2) ? 0 : n_iter); it += nwarps) {
+    const int u = strided ? lane * n_iter + (int)it : (int)it * 32 + lane;
     int tok = 0, f = 0, base = 0, cnt = 0;
     if (u < nu) {
       f = __ldg(plan.uniq_attr + u);
@@ -1024,7 +1033,8 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
             V<VEC>::sgd(Ev[q], gq, lr);
             V<VEC>::st(s_attrs[fq[q]].table + off, Ev[q]);
           } else {
-            V<VEC>::st(rows_out + ((size_t)u0 + r + q) * dim + (size_t)col * VEC, gq);
+            const size_t urow = strided ? (size_t)(r + q) * n_iter + (size_t)it : (size_t)it * 32 + r + q;   // row of lane r + q
+            V<VEC>::st(rows_out + urow * dim + (size_t)col * VEC, gq);
           }
         }
       }
@@ -1036,8 +1046,11 @@ pool_bwd_apply_body(const arx_attr_desc* __restrict__ s_attrs, int dim,
   }
 }
 
+#ifndef ARX_APPLY_MINB
+#define ARX_APPLY_MINB 2
+#endif
 template <int VEC, bool FLAT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, ARX_APPLY_MINB)
 pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim,
                        arx_bwd_plan plan, const float* __restrict__ dout, long long dout_stride,
                        const float* __restrict__ dbias, float lr,
@@ -1149,7 +1162,9 @@ int g_tune_flat_epb = 0;         // arx_set_tuning("flat_epb", 0 = auto | 1..16)
 int g_tune_apply_cps = 4;        // arx_set_tuning("apply_ctas_per_sm", 1..4)
 int g_tune_heavy = 64;          // arx_set_tuning("heavy", 8..64): bucket size above which a row is split across warps; must not change
                                 // between building a plan and applying it; arx_bwd_plan.cap_chunks >= 2 * cap_occ / heavy + 1
-int g_tune_apply_flat = 1;      // arx_set_tuning("apply_flat", 0 | 1): pre-loaded flat bucket entries in the row phase of the apply kernel
+int g_tune_apply_phase_off = 0; // measurement only: bit 0 skips the hot-row chunk phase, bit 1 the row phase (results are then WRONG)
+int g_tune_apply_contig = 0;    // arx_set_tuning("apply_contig", 1): A/B switch back to 32 CONSECUTIVE unique rows per warp iteration
+int g_tune_apply_flat = 0;      // arx_set_tuning("apply_flat", 0 | 1): pre-loaded flat bucket entries in the row phase of the apply kernel
 int g_tune_plan_agg = 3;         // arx_set_tuning("plan_agg", 0 | 1): block-aggregated plan_count / plan_fill (tables < 2^27 rows)
 
 inline int pick_grid(long long warps_needed, int threads) {
@@ -1379,13 +1394,13 @@ extern "C" int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int di
   const bool v4 = (dim % 4 == 0) && (dout_stride % 4 == 0) && (((uintptr_t)dout & 15) == 0);
   if (v4 && g_tune_apply_flat)
     pool_bwd_apply_kernel<4, true><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                          dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
+                                                          dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy | (g_tune_apply_phase_off << 8) | (g_tune_apply_contig << 10));
   else if (v4)
     pool_bwd_apply_kernel<4, false><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
+                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy | (g_tune_apply_phase_off << 8) | (g_tune_apply_contig << 10));
   else
     pool_bwd_apply_kernel<1, false><<<grid, 256, 0, st>>>(attrs, n_attr, dim, plan, dout, (long long)dout_stride,
-                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy);
+                                                           dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, g_tune_heavy | (g_tune_apply_phase_off << 8) | (g_tune_apply_contig << 10));
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }
@@ -1430,12 +1445,20 @@ extern "C" int arx_set_tuning(const char* key, int value) {
     g_tune_heavy = value;
     return ARX_OK;
   }
+  if (eq("apply_phase_off")) {
+    g_tune_apply_phase_off = value & 3;
+    return ARX_OK;
+  }
+  if (eq("apply_contig")) {
+    g_tune_apply_contig = value & 1;
+    return ARX_OK;
+  }
   if (eq("apply_flat")) {
     g_tune_apply_flat = value & 1;
     return ARX_OK;
   }
   if (eq("apply_ctas_per_sm")) {
-    if (value < 1 || value > 4) return ARX_E_BADARG;
+    if (value < 1 || value > 8) return ARX_E_BADARG;
     g_tune_apply_cps = value;
     return ARX_OK;
   }

@@ -30,6 +30,12 @@ class PoolReq(ctypes.Structure):
                 ('out_stride', ctypes.c_int64), ('n_attr', ctypes.c_int32), ('max_rows_per_entity', ctypes.c_int32)]
 
 
+class PoolPush(ctypes.Structure):
+    """arx_pool_push (include/arx_b200.h)."""
+    _fields_ = [('peer_out', vp), ('rows_per_rank', ctypes.c_int64), ('stride', ctypes.c_int64),
+                ('bias_col', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
 class BwdPlan(ctypes.Structure):
     """arx_bwd_plan (include/arx_b200.h)."""
     _fields_ = [('counters', vp), ('uniq_tok', vp), ('uniq_attr', vp), ('row_base', vp),
@@ -85,6 +91,14 @@ SIGNATURES = {
     'arx_pool_fwd_many': [vp, i32, i32, vp],
     'arx_mw_prep': [vp, vp, f32, vp, vp, vp, vp, vp, i64, i64, i32, vp, vp, vp, vp, vp, vp, vp],
     'arx_mw_post': [vp, vp, vp, vp, vp, f32, i64, i32, vp, vp, vp, vp],
+    'arx_pool_fwd_many_push': [vp, vp, i32, i32, vp],
+    'arx_peer_alloc': [i64, vp],
+    'arx_peer_free': [vp],
+    'arx_peer_export': [vp, vp],
+    'arx_peer_open': [vp, vp],
+    'arx_peer_close': [vp],
+    'arx_peer_barrier': [vp, i32, i32, vp, i64, vp, vp],
+    'arx_peer_push_rows': [vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, vp],
     'arx_score_max': [vp, vp, i64, i64, vp, vp],
     'arx_token_pool_fwd': [vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp],
     'arx_token_pool_bwd': [vp, vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp, vp],

@@ -1019,24 +1019,41 @@ class EmbeddingAttribute(object):
             a0, na = self.sets[prefix].attr_range(kw.get('no_id', False), kw.get('no_attribute', False))
             width = self.dim if mode == POOL_MEAN else self.dim * na
             o = kw.get('out')              # optional: pool straight into a (row-strided) view of a caller's buffer
+            if kw.get('push') is not None:
+                outs.append((None, None))  # results are ADDED into the owner ranks' receive blocks (hmf/exchange.py::PeerExchange)
+                continue
             if o is None:
                 o = torch.empty((ids.numel(), width), dtype=torch.float32, device=self.device)
             outs.append((o, torch.empty((ids.numel(),), dtype=torch.float32, device=self.device) if want_bias else None))
-        if (len(requests) > 1 and len(requests) <= 4 and self.dim in (128, 256)
+        pushing = any(r[4].get('push') is not None for r in requests)
+        if pushing and not (len(requests) <= 4 and self.dim in (128, 256) and all(r[2] == POOL_MEAN for r in requests)):
+            raise NotImplementedError('push-mode lookups need mean pooling and dim 128 / 256')
+        if pushing or (len(requests) > 1 and len(requests) <= 4 and self.dim in (128, 256)
                 and all(r[2] == POOL_MEAN for r in requests) and os.environ.get('ARX_POOL_MANY', '1') == '1'):
             # all lookups of the step in ONE launch (arx_pool_fwd_many): one ramp, one tail, balanced waves
             reqs = (_lib.PoolReq * len(requests))()
+            push = (_lib.PoolPush * len(requests))()
             rngs = []
             for k, ((prefix, ids, mode, want_bias, kw), (o, b)) in enumerate(zip(requests, outs)):
                 ts = self.sets[prefix]
                 a0, na = ts.attr_range(kw.get('no_id', False), kw.get('no_attribute', False))
                 rngs.append((a0, na))
                 q = reqs[k]
-                q.attrs, q.ent_ids, q.out = ts.desc_ptr(a0), ids.data_ptr(), o.data_ptr()
-                q.bias_out = b.data_ptr() if want_bias else None
-                q.n, q.out_stride, q.n_attr = ids.numel(), o.stride(0), na
+                q.attrs, q.ent_ids = ts.desc_ptr(a0), ids.data_ptr()
+                q.n, q.n_attr = ids.numel(), na
                 q.max_rows_per_entity = int(sum(ts.max_len[a0:a0 + na]))
+                if kw.get('push') is not None:
+                    peers, rows_per_rank, pitch, bias_col = kw['push']
+                    push[k].peer_out, push[k].rows_per_rank, push[k].stride = peers.data_ptr(), rows_per_rank, pitch
+                    push[k].bias_col = bias_col if want_bias else -1
+                    q.out, q.bias_out, q.out_stride = None, None, pitch
+                else:
+                    q.out, q.out_stride = o.data_ptr(), o.stride(0)
+                    q.bias_out = b.data_ptr() if want_bias else None
             _lib.tag = 'many'
+            if pushing:
+                call('arx_pool_fwd_many_push', ctypes.addressof(reqs), ctypes.addressof(push), len(requests), self.dim)
+                return [(o, b, rg) for (o, b), rg in zip(outs, rngs)]
             if call('arx_pool_fwd_many', ctypes.addressof(reqs), len(requests), self.dim) == 0:
                 return [(o, b, rg) for (o, b), rg in zip(outs, rngs)]
         res, forks = [], []

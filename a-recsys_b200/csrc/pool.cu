@@ -216,11 +216,28 @@ constexpr int kFlatEnt = 16;         // entities per CTA pass
 constexpr int kFlatRows = 1024;
 constexpr int kFlatU = 8;
 
+// Push mode (row-sharded tables): instead of storing this rank's PARTIAL pooled vectors into a local
+// [n, stride] buffer that a reduce-scatter would then sum over the ranks, pass 3 adds them straight into the OWNER
+// rank's receive buffer over NVLink peer memory (entity e belongs to rank e / rows_per_rank; red.global.add.v4.f32,
+// system scope).  The receive buffers are zero before the step; a device-side barrier (csrc/peer.cu) orders the adds
+// before the consumer.  Entities none of whose rows live here cause no traffic at all.
+struct PushDesc {
+  float* const* peer;        // device array [G]: base of every rank's receive block for this request (NULL = no push)
+  long long rows_per_rank;   // entities per owner rank
+  long long stride;          // row pitch of the receive blocks, floats
+  int bias_col;              // column (float index) of the pooled bias inside the receive row, or -1
+};
+
+__device__ __forceinline__ void red_add_f4_sys(float* p, float4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 template <int CPL>      // float4 columns per lane: dim = 128 * CPL
 __device__ __forceinline__ void
 pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
                    long long n, float* __restrict__ out, long long out_stride,
-                   float* __restrict__ bias_out, int epb, long long vblock, long long vgrid) {
+                   float* __restrict__ bias_out, int epb, long long vblock, long long vgrid, const PushDesc push) {
   constexpr int dim = 128 * CPL;
   extern __shared__ __align__(16) unsigned char s_raw[];
   __shared__ int s_start[kFlatBags], s_len[kFlatBags], s_off[kFlatBags + 1];
@@ -357,7 +374,11 @@ pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const 
           for (int w = wlo; w <= whi; ++w)               // fixed warp order
             f4_add(tot, ld_f4(s_part + ((size_t)w * 2 + (w < whi ? 1 : 0)) * dim + (size_t)col * 4));
       }
-      st_f4(out + (e0 + el) * out_stride + (size_t)col * 4, tot);
+      if (push.peer == nullptr) st_f4(out + (e0 + el) * out_stride + (size_t)col * 4, tot);
+      else if (L > 0) {
+        const long long owner = (e0 + el) / push.rows_per_rank;
+        red_add_f4_sys(push.peer[owner] + ((e0 + el) - owner * push.rows_per_rank) * push.stride + (size_t)col * 4, tot);
+      }
     }
     if (want_bias && tid < ne) {
       const int o = s_off[tid * n_attr], L = s_off[(tid + 1) * n_attr] - o;
@@ -367,7 +388,12 @@ pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const 
         if (wlo == whi) bt = s_bias[tid];
         else for (int w = wlo; w <= whi; ++w) bt += s_partb[w][w < whi ? 1 : 0];
       }
-      bias_out[e0 + tid] = bt;                                                            // :404-412
+      if (push.peer == nullptr) bias_out[e0 + tid] = bt;                                  // :404-412
+      else if (L > 0 && push.bias_col >= 0) {
+        const long long owner = (e0 + tid) / push.rows_per_rank;
+        asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(push.peer[owner] + ((e0 + tid) - owner * push.rows_per_rank) *
+                                                                       push.stride + push.bias_col), "f"(bt) : "memory");
+      }
     }
     __syncthreads();
    }
@@ -379,7 +405,7 @@ __global__ void __launch_bounds__(256, CPL == 1 ? 4 : 2)
 pool_fwd_flat_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const int* __restrict__ ids,
                      long long n, float* __restrict__ out, long long out_stride,
                      float* __restrict__ bias_out, int epb) {
-  pool_fwd_flat_body<CPL>(g_attrs, n_attr, ids, n, out, out_stride, bias_out, epb, blockIdx.x, gridDim.x);
+  pool_fwd_flat_body<CPL>(g_attrs, n_attr, ids, n, out, out_stride, bias_out, epb, blockIdx.x, gridDim.x, PushDesc{});
 }
 
 // Several independent lookups (e.g. the users, the target items and the sampled pool of one training step) in ONE
@@ -396,6 +422,7 @@ struct PoolManyParams {
   int n_attr[kManyReqs];
   int epb[kManyReqs];
   int block_end[kManyReqs];        // exclusive prefix of CTAs per request
+  PushDesc push[kManyReqs];
   int n_req;
 };
 
@@ -406,7 +433,7 @@ pool_fwd_flat_many_kernel(const PoolManyParams mp) {
   while (r + 1 < mp.n_req && (int)blockIdx.x >= mp.block_end[r]) ++r;
   const int b0 = r == 0 ? 0 : mp.block_end[r - 1];
   pool_fwd_flat_body<CPL>(mp.attrs[r], mp.n_attr[r], mp.ids[r], mp.n[r], mp.out[r], mp.out_stride[r], mp.bias_out[r],
-                          mp.epb[r], (long long)blockIdx.x - b0, (long long)(mp.block_end[r] - b0));
+                          mp.epb[r], (long long)blockIdx.x - b0, (long long)(mp.block_end[r] - b0), mp.push[r]);
 }
 
 // integer part of K2 (mulhot_index.py:48-67)
@@ -1249,7 +1276,7 @@ extern "C" int arx_pool_fwd(const arx_attr_desc* attrs, int n_attr, int dim, con
 
 // K1+K2 for several independent lookups in one launch (mean mode, dim 128 / 256, every request within the flat
 // kernel's limits); ARX_E_UNSUPPORTED otherwise: the caller then issues one arx_pool_fwd per lookup.
-extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream) {
+static int pool_fwd_many_impl(const arx_pool_req* reqs, const arx_pool_push* push, int n_req, int dim, void* stream) {
   if (!reqs || n_req < 1 || n_req > kManyReqs) return ARX_E_BADARG;
   if (dim != 128 && dim != 256) return ARX_E_UNSUPPORTED;
   PoolManyParams mp{};
@@ -1259,9 +1286,12 @@ extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, v
   int max_attr = 0, k = 0;
   for (int i = 0; i < n_req; ++i) {
     const arx_pool_req& q = reqs[i];
-    if (!q.attrs || !q.ent_ids || !q.out || q.n_attr < 1 || q.n_attr > kMaxAttr || q.n < 0) return ARX_E_BADARG;
-    if (q.n_attr > kFlatBags || q.max_rows_per_entity <= 0 || q.max_rows_per_entity > kFlatRows || (q.out_stride % 4) ||
-        ((uintptr_t)q.out & 15))
+    const bool pushed = push != nullptr && push[i].peer_out != nullptr;
+    if (!q.attrs || !q.ent_ids || (!q.out && !pushed) || q.n_attr < 1 || q.n_attr > kMaxAttr || q.n < 0) return ARX_E_BADARG;
+    if (pushed && (push[i].rows_per_rank < 1 || push[i].stride < dim || (push[i].stride % 4) || push[i].bias_col >= push[i].stride))
+      return ARX_E_BADARG;
+    if (q.n_attr > kFlatBags || q.max_rows_per_entity <= 0 || q.max_rows_per_entity > kFlatRows ||
+        (!pushed && ((q.out_stride % 4) || ((uintptr_t)q.out & 15))))
       return ARX_E_UNSUPPORTED;
     total_n += q.n;
     max_attr = std::max(max_attr, q.n_attr);
@@ -1278,6 +1308,13 @@ extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, v
     if (g_tune_flat_epb > 0 && g_tune_flat_epb < epb) epb = g_tune_flat_epb;
     mp.attrs[k] = q.attrs; mp.ids[k] = q.ent_ids; mp.out[k] = q.out; mp.bias_out[k] = q.bias_out;
     mp.n[k] = q.n; mp.out_stride[k] = q.out_stride; mp.n_attr[k] = q.n_attr; mp.epb[k] = epb;
+    mp.push[k] = PushDesc{};
+    if (push != nullptr && push[i].peer_out != nullptr) {
+      mp.push[k].peer = push[i].peer_out; mp.push[k].rows_per_rank = push[i].rows_per_rank;
+      mp.push[k].stride = push[i].stride; mp.push[k].bias_col = push[i].bias_col;
+      // in push mode the pooled bias goes to column bias_col of the receive row; bias_out only says "bias wanted"
+      mp.bias_out[k] = push[i].bias_col >= 0 ? reinterpret_cast<float*>(16) : nullptr;
+    }
     blocks += (int)std::min<long long>((q.n + epb - 1) / epb, slots * 4);
     mp.block_end[k] = blocks;
     ++k;
@@ -1295,6 +1332,17 @@ extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, v
   }
   ARX_CHECK_LAUNCH();
   return ARX_OK;
+}
+
+extern "C" int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream) {
+  return pool_fwd_many_impl(reqs, nullptr, n_req, dim, stream);
+}
+
+// The same launch with the results of the requests whose push[i].peer_out is set ADDED into the owner ranks' receive
+// buffers over NVLink peer memory (see PushDesc) instead of stored locally: lookup + reduce-scatter in one kernel.
+extern "C" int arx_pool_fwd_many_push(const arx_pool_req* reqs, const arx_pool_push* push, int n_req, int dim, void* stream) {
+  if (!push) return ARX_E_BADARG;
+  return pool_fwd_many_impl(reqs, push, n_req, dim, stream);
 }
 
 extern "C" int arx_mulhot_flat_index(const arx_attr_desc* attrs, int attr, const int32_t* ent_ids,

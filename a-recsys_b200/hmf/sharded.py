@@ -16,7 +16,9 @@ from .exchange import RowShardExchange
 
 
 class ShardedLatentProductModel(LatentProductModel):
-    def __init__(self, *a, group=None, **kw):
+    def __init__(self, *a, group=None, peer=None, **kw):
+        """peer: True / False forces the NVLink peer-memory exchange on / off; None = on unless ARX_PEER=0."""
+        self._peer_pref = peer
         self.ex = RowShardExchange(group)
         kw['shard'] = (self.ex.G, self.ex.r)
         super(ShardedLatentProductModel, self).__init__(*a, **kw)
@@ -41,6 +43,8 @@ class ShardedLatentProductModel(LatentProductModel):
         mb = n_g // G
         S = m.sampled_ids.numel()
         pre = m._out_prefix()
+        if self._peer_ok(mb, S, d):
+            return self._step_peer(users_g, items_g, mb, S, masks, sync)
         # ---- forward: partial pooling of owned rows, one RS + one AR --------------------------
         # one packed exchange buffer per collective; row pitch 2d + 4 keeps every block 16-byte aligned so that the
         # lookups pool STRAIGHT into it (no staging copies): [ user vector | target-item vector | target bias, pad ]
@@ -145,6 +149,110 @@ class ShardedLatentProductModel(LatentProductModel):
         if not sync:
             return loss_sum
         ex.all_reduce(loss_sum)
+        return float(loss_sum.item())
+
+    # ---- the same step over NVLink peer memory (hmf/exchange.py::PeerExchange) ---------------------------------
+    def _peer_ok(self, mb, S, d):
+        """Peer-memory exchange: NCCL backend (one GPU per rank on one node), the fused glue's shapes, not switched off
+        (ARX_PEER=0 keeps the NCCL collectives for A/B runs)."""
+        if getattr(self, 'px', None) is not None:
+            return self.px.mb == mb and self.px.S == S
+        if getattr(self, '_peer_tried', False):
+            return False
+        self._peer_tried = True
+        import os
+        want = self._peer_pref if self._peer_pref is not None else os.environ.get('ARX_PEER', '1') == '1'
+        if not self.ex.nccl or not want or self.att_emb.dim not in (128, 256):
+            return False
+        if not (_lib.ce_supported(mb, S, d) and d % 4 == 0):
+            return False
+        from .exchange import PeerExchange
+        self.px = PeerExchange(self.ex.group, self.device, mb, S, d)
+        return True
+
+    def _step_peer(self, users_g, items_g, mb, S, masks, sync):
+        m, px = self.att_emb, self.px
+        G, r, d = px.G, px.r, self.size
+        dev = self.device
+        n_g = users_g.numel()
+        pre = m._out_prefix()
+        f32 = dict(dtype=torch.float32, device=dev)
+        px.dsp.zero_()                                              # cleared before this step's first barrier
+        irng0 = m.sets[pre].attr_range()
+        m.prefetch_plans({'user': [(m.sets['user'].attr_range(), users_g, POOL_MEAN)],
+                          pre: [(irng0, m.sampled_ids, POOL_MEAN), (irng0, items_g, POOL_MEAN)]})
+        # lookups: partial sums of the rows this rank owns, for ALL G*mb bags, added straight into the owners' `loc`
+        # blocks (lookup + reduce-scatter in one kernel); the pool partials go to every rank's `sp` block
+        sp_part = torch.empty((S, px.Wp), **f32)
+        (_, _, urng), (_, _, irng), (ps, bs, _) = m.pool_many([
+            ('user', users_g, POOL_MEAN, False, {'push': px.push_desc('user')}),
+            (pre, items_g, POOL_MEAN, True, {'push': px.push_desc('item')}),
+            (pre, m.sampled_ids, POOL_MEAN, True, {'out': sp_part[:, :d]})])
+        sp_part[:, d] = bs
+        sp_part[:, d + 1:] = 0
+        px.add_to_all(sp_part, 'sp')
+        px.barrier()                                                # B1: every rank's pushes have landed
+        loc, sp = px.loc, px.sp
+        U0, Pt, btl = loc[:, :d], loc[:, d:2 * d], loc[:, 2 * d]
+        Ps = sp[:, :d].contiguous()
+        bsl = sp[:, d].contiguous()
+        U0 = U0.contiguous(); Pt = Pt.contiguous(); btl = btl.contiguous()
+        users_l = users_g[r * mb:(r + 1) * mb].contiguous()
+        keep = self.dropout
+        scale = self._scale(n_g)[:mb]                               # 1 / (G*mb): global batch mean
+        u = torch.empty((mb, d), **f32); U_r = torch.empty((mb, d), **f32); UT = torch.empty((d, mb), **f32)
+        P_r = torch.empty((S, d), **f32); PT = torch.empty((d, S), **f32)
+        tscore = torch.empty((mb,), **f32)
+        inv_keep = 1.0 / keep
+        dmask = drng = dmask_out = None
+        if keep != 1.0:
+            if masks:
+                dmask = masks[0]
+            else:
+                if not hasattr(self, '_drop_rng'):
+                    seed = int(torch.randint(0, 2 ** 31 - 1, (1,)).item()) + 7919 * r            # a different stream per rank
+                    self._drop_rng = torch.tensor([seed, 0], dtype=torch.int64, device=dev)
+                drng = self._drop_rng
+                dmask_out = torch.empty((mb, d), **f32)
+        call('arx_mw_prep', U0.data_ptr(), _lib.ptr(dmask), inv_keep, _lib.ptr(drng), _lib.ptr(dmask_out), Pt.data_ptr(),
+             btl.data_ptr(), Ps.data_ptr(), mb, S, d, u.data_ptr(), U_r.data_ptr(), UT.data_ptr(), tscore.data_ptr(),
+             P_r.data_ptr(), PT.data_ptr())
+        if drng is not None:
+            dmask = dmask_out
+        fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l, prepared=(U_r, P_r, UT, PT))
+        if fused is None:
+            raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
+        bl, (dU, dPs, dbs, dts) = fused
+        loss_sum = (bl.sum() / n_g).reshape(1)
+        dU0 = torch.empty((mb, d), **f32)
+        dPt = torch.empty((mb, d), **f32)
+        call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), _lib.ptr(dmask), inv_keep, mb, d,
+             dU0.data_ptr(), dPt.data_ptr(), _lib.ptr(drng))
+        # backward exchange: gradient rows stored into every rank's `back`, pool gradients added into every rank's `dsp`
+        mine = torch.empty((mb, px.W), **f32)
+        mine[:, :d] = dU0
+        mine[:, d:2 * d] = dPt
+        mine[:, 2 * d] = dts
+        mine[:, 2 * d + 1:] = 0
+        px.gather_rows(mine)
+        dsp_in = torch.empty((S, px.Wp), **f32)
+        dsp_in[:, :d] = dPs
+        dsp_in[:, d] = dbs
+        dsp_in[:, d + 1:] = 0
+        px.add_to_all(dsp_in, 'dsp')
+        px.loc.zero_()                                              # consumed: cleared before this step's second barrier
+        px.sp.zero_()
+        px.barrier()                                                # B2
+        back, dsp = px.back, px.dsp
+        m.push_grad('user', urng, users_g, POOL_MEAN, back[:, :d])
+        rng = m.sets[pre].attr_range()
+        m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, dsp[:, :d].contiguous(), dsp[:, d].contiguous())
+        m.push_grad(pre, rng, items_g, POOL_MEAN, back[:, d:2 * d].contiguous(), back[:, 2 * d].contiguous())
+        m.apply_gradients(self.learning_rate.eval(), OPT_ADAGRAD)
+        self.global_step.assign(self.global_step.eval() + 1)
+        if not sync:
+            return loss_sum
+        self.ex.all_reduce(loss_sum)
         return float(loss_sum.item())
 
     def replay_step(self, users, items, sync=True):

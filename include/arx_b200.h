@@ -86,6 +86,34 @@ typedef struct arx_pool_req {
 } arx_pool_req;
 int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream);
 
+/* K11 — row-sharded tables over NVLink peer memory (the reference is single-GPU, nearest analogue: the
+ * tower-wise tf.device placement at lstm/run.py:221-229).  One process per GPU; every rank allocates its receive
+ * buffers with arx_peer_alloc, exports them (CUDA IPC, 64-byte handle) and maps the other ranks' (arx_peer_open).
+ * arx_pool_fwd_many_push is arx_pool_fwd_many with the PARTIAL pooled vectors of request i ADDED (red.global.add.v4.f32,
+ * system scope) into the owner rank's receive block instead of stored locally: entity e belongs to rank
+ * e / rows_per_rank, row e % rows_per_rank of peer_out[owner] (row pitch `stride` floats, pooled bias added to column
+ * bias_col when >= 0) — lookup + reduce-scatter in one kernel; the receive blocks must be zero before the step.
+ * arx_peer_push_rows copies (mode 0, rank `skip` left out) or adds (mode 1) rows into rows [row0, row0 + rows) of
+ * every rank's block (all-gather / all-reduce by push).  arx_peer_barrier: device-side barrier over the G ranks
+ * (flags[g] = rank g's block of >= G uint32, epoch = this rank's device counter), stream-ordered and graph-capturable;
+ * a rank that waits longer than timeout_ns stores 1 + the missing rank into *err instead of spinning forever. */
+typedef struct arx_pool_push {
+  float* const* peer_out;          /* device array [G] of receive-block bases, or NULL: store to arx_pool_req.out */
+  int64_t rows_per_rank;
+  int64_t stride;
+  int32_t bias_col;
+  int32_t reserved;
+} arx_pool_push;
+int arx_pool_fwd_many_push(const arx_pool_req* reqs, const arx_pool_push* push, int n_req, int dim, void* stream);
+int arx_peer_alloc(int64_t bytes, void** ptr);
+int arx_peer_free(void* ptr);
+int arx_peer_export(void* ptr, unsigned char* handle64);
+int arx_peer_open(const unsigned char* handle64, void** ptr);
+int arx_peer_close(void* ptr);
+int arx_peer_barrier(uint32_t* const* flags, int rank, int G, uint32_t* epoch, int64_t timeout_ns, int32_t* err, void* stream);
+int arx_peer_push_rows(const float* src, int64_t rows, int64_t width, int64_t src_stride, float* const* dst,
+                       int64_t dst_stride, int64_t row0, int G, int skip, int mode, void* stream);
+
 /* Integer part of K2 only (mulhot_index.py:48-67): flat token index and segment id
  * vectors for one multi-hot attribute; bit-exact parity target.  offsets[n+1] is an
  * exclusive scan of the bag lengths computed by the caller (device). */

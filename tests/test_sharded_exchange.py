@@ -131,3 +131,74 @@ def test_sharded_hmf_matches_oracle_two_gpus():
     for p in procs:
         p.join(timeout=60)
     assert all(r[1] for r in res), res
+
+
+def _peer_worker(rank, world, port, q):
+    """NVLink peer-memory exchange (arx_pool_fwd_many_push + arx_peer_push_rows + arx_peer_barrier) against the NCCL
+    collectives on the same sharded model, and against the oracle at the global batch."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
+    os.environ['ARX_PEER_TIMEOUT_S'] = '30'
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    try:
+        import arecsys_b200  # noqa: F401
+        from arecsys_b200.hmf.sharded import ShardedLatentProductModel
+        from oracle import np_oracle as O
+        from helpers import small_dataset, random_params, positives
+        dim, nu, ni = 128, 300, 200
+        ua, ia, _, l2i = small_dataset(nu, ni, 3, 50, 4, 8, 0, None, dim)
+        params = random_params(ua, ia, dim, 1, scale=0.1)
+        l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
+        i2l_d = {v: k for k, v in l2i_d.items()}
+        mb, ns = 64, 64
+        mk = lambda peer: ShardedLatentProductModel(nu, ni, dim, 1, mb, 0.3, 1.0, ua, ia, i2l_d, l2i_d, loss_function='mw',
+                                                    dropout=0.5, n_sampled=ns, params={k: v.copy() for k, v in params.items()},
+                                                    peer=peer)
+        A, B = mk(True), mk(False)
+        emb = O.OracleEmbeddingAttribute(ua, ia, world * mb, ns, {k: v.copy() for k, v in params.items()},
+                                         item_ind2logit_ind=i2l_d, logit_ind2item_ind=l2i_d)
+        om = O.OracleHMF(emb, loss='mw', keep_prob=0.5, learning_rate=0.3)
+        rng = np.random.default_rng(5)
+        ok, detail = True, []
+        for it in range(4):
+            users = rng.integers(0, nu, world * mb); items = rng.integers(0, ni, world * mb)
+            pos = positives(users, items, nu, rng, n_items=ni)
+            for mdl in (A, B):
+                mdl.prepare_warp(pos, pos)
+            emb.prepare_warp(pos, pos)
+            sampled = [int(v) for v in rng.permutation(ni)[:ns]] if it != 1 else None
+            id2idx = {v: k for k, v in enumerate(sampled)} if sampled else None
+            mask = np.floor(rng.random((world * mb, dim)) + 0.5)
+            mk_ = [torch.tensor(mask[rank * mb:(rank + 1) * mb], dtype=torch.float32, device='cuda')]
+            la = A.step(None, users.tolist(), items.tolist(), None, sampled, id2idx, loss='mw', masks=mk_)
+            lb = B.step(None, users.tolist(), items.tolist(), None, sampled, id2idx, loss='mw', masks=mk_)
+            lo = om.step(users.tolist(), items.tolist(), sampled, id2idx, masks=[mask])
+            A.px.check()
+            ok = ok and getattr(B, 'px', None) is None and abs(la - lb) <= 1e-6 * max(1.0, abs(lb)) and abs(la - lo) <= 2e-3 * max(1.0, abs(lo))
+            detail.append((la, lb, lo))
+            for k in A.att_emb.params:
+                a_, b_ = A.att_emb.params[k], B.att_emb.params[k]
+                ok = ok and bool(torch.allclose(a_, b_, rtol=1e-5, atol=1e-7))
+                v = om.emb.p[k]
+                ok = ok and np.allclose(a_.cpu().numpy(), v[rank::world].reshape(a_.shape), rtol=2e-2, atol=2e-4)
+        q.put((rank, bool(ok), detail))
+    except Exception as e:           # noqa: BLE001  (the parent must hear about it instead of waiting for the queue)
+        import traceback
+        q.put((rank, False, traceback.format_exc()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_peer_memory_exchange_matches_nccl_and_oracle_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res), res

@@ -32,8 +32,14 @@ class PoolReq(ctypes.Structure):
 
 class PoolPush(ctypes.Structure):
     """arx_pool_push (include/arx_b200.h)."""
-    _fields_ = [('peer_out', vp), ('rows_per_rank', ctypes.c_int64), ('stride', ctypes.c_int64),
-                ('bias_col', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+    _fields_ = [('peer_out', vp), ('peer_bias', vp), ('rows_per_rank', ctypes.c_int64), ('stride', ctypes.c_int64),
+                ('n_ranks', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+
+class PeerSeg(ctypes.Structure):
+    """arx_peer_seg (include/arx_b200.h)."""
+    _fields_ = [('src', vp), ('dst', vp), ('rows', ctypes.c_int64), ('width', ctypes.c_int64), ('src_stride', ctypes.c_int64),
+                ('dst_stride', ctypes.c_int64), ('row0', ctypes.c_int64), ('mode', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class BwdPlan(ctypes.Structure):
@@ -99,6 +105,7 @@ SIGNATURES = {
     'arx_peer_close': [vp],
     'arx_peer_barrier': [vp, i32, i32, vp, i64, vp, vp],
     'arx_peer_push_rows': [vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, vp],
+    'arx_peer_push_many': [vp, i32, i32, vp],
     'arx_score_max': [vp, vp, i64, i64, vp, vp],
     'arx_token_pool_fwd': [vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp],
     'arx_token_pool_bwd': [vp, vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp, vp],

@@ -843,21 +843,18 @@ class EmbeddingAttribute(object):
 
     @staticmethod
     def _adjacent(parts):
-        """If the tensors are consecutive contiguous slices of one buffer (the caller wrote its gradients
+        """If the tensors are consecutive contiguous row blocks of one allocation (the caller wrote its gradients
         straight into a shared arena), return the covering view instead of concatenating."""
-        base = getattr(parts[0], '_base', None)
-        if base is None or not base.is_contiguous() or base.dim() != parts[0].dim():
-            return None
-        p = parts[0].data_ptr()
-        if p != base.data_ptr():
-            return None
-        n = 0
+        p0 = parts[0]
+        st = p0.untyped_storage().data_ptr()
+        p, n = p0.data_ptr(), 0
         for t in parts:
-            if getattr(t, '_base', None) is not base or not t.is_contiguous() or t.data_ptr() != p:
+            if (not t.is_contiguous() or t.shape[1:] != p0.shape[1:] or t.dtype != p0.dtype or t.data_ptr() != p
+                    or t.untyped_storage().data_ptr() != st):
                 return None
             p += t.numel() * t.element_size()
             n += t.shape[0]
-        return base if n == base.shape[0] else base[:n]
+        return torch.as_strided(p0, (n,) + tuple(p0.shape[1:]), p0.stride())
 
     def _merge_dense(self):
         """Tables that hold a dense gradient (token_prediction_backward) AND pending look-up gradients get ONE summed dense
@@ -1043,9 +1040,10 @@ class EmbeddingAttribute(object):
                 q.n, q.n_attr = ids.numel(), na
                 q.max_rows_per_entity = int(sum(ts.max_len[a0:a0 + na]))
                 if kw.get('push') is not None:
-                    peers, rows_per_rank, pitch, bias_col = kw['push']
+                    peers, peers_bias, rows_per_rank, pitch, n_ranks = kw['push']
                     push[k].peer_out, push[k].rows_per_rank, push[k].stride = peers.data_ptr(), rows_per_rank, pitch
-                    push[k].bias_col = bias_col if want_bias else -1
+                    push[k].peer_bias = peers_bias.data_ptr() if (want_bias and peers_bias is not None) else None
+                    push[k].n_ranks = n_ranks
                     q.out, q.bias_out, q.out_stride = None, None, pitch
                 else:
                     q.out, q.out_stride = o.data_ptr(), o.stride(0)

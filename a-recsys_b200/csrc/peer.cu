@@ -73,7 +73,64 @@ peer_push_rows_kernel(const float* __restrict__ src, long long rows, int width4,
   }
 }
 
+// Several row blocks in one launch (the backward exchange of a step: dU | dPt | dts stored, dPs | dbs added): each
+// segment owns a contiguous range of CTAs proportional to its size.
+constexpr int kPushSegs = 8;
+struct PushManyParams {
+  arx_peer_seg seg[kPushSegs];
+  int block_end[kPushSegs];
+  int n_segs, G;
+};
+
+__global__ void __launch_bounds__(256) peer_push_many_kernel(const PushManyParams mp) {
+  int s = 0;
+  while (s + 1 < mp.n_segs && (int)blockIdx.x >= mp.block_end[s]) ++s;
+  const int b0 = s == 0 ? 0 : mp.block_end[s - 1];
+  const arx_peer_seg& sg = mp.seg[s];
+  const int width4 = (int)(sg.width >> 2);
+  const int G = mp.G;
+  const long long total = sg.rows * width4 * G;
+  const long long nthreads = (long long)(mp.block_end[s] - b0) * blockDim.x;
+  for (long long i = (long long)(blockIdx.x - b0) * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const long long slab = i / width4;
+    const int c = (int)(i - slab * width4);
+    const int g = (int)(slab % G);
+    const long long r = slab / G;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(sg.src + r * sg.src_stride) + c);
+    float* p = sg.dst[g] + (sg.row0 + r) * sg.dst_stride + (long long)c * 4;
+    if (sg.mode == 0) {
+      asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    } else {
+      asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                   : "memory");
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" int arx_peer_push_many(const arx_peer_seg* segs, int n_segs, int G, void* stream) {
+  if (!segs || n_segs < 1 || n_segs > kPushSegs || G < 1) return ARX_E_BADARG;
+  PushManyParams mp{};
+  int blocks = 0, k = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    const arx_peer_seg& q = segs[i];
+    if (!q.src || !q.dst || q.rows < 0 || q.width < 4 || (q.width % 4) || (q.src_stride % 4) || (q.dst_stride % 4) ||
+        (((uintptr_t)q.src) & 15) || q.mode < 0 || q.mode > 1)
+      return ARX_E_BADARG;
+    if (q.rows == 0) continue;
+    const long long total = q.rows * (q.width / 4) * G;
+    blocks += (int)std::min<long long>((total + 1023) / 1024, (long long)arx_num_sms() * 4);
+    mp.seg[k] = q;
+    mp.block_end[k] = blocks;
+    ++k;
+  }
+  if (k == 0) return ARX_OK;
+  mp.n_segs = k; mp.G = G;
+  peer_push_many_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mp);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
 
 extern "C" int arx_peer_alloc(int64_t bytes, void** ptr) {
   if (!ptr || bytes <= 0) return ARX_E_BADARG;

@@ -223,9 +223,10 @@ constexpr int kFlatU = 8;
 // before the consumer.  Entities none of whose rows live here cause no traffic at all.
 struct PushDesc {
   float* const* peer;        // device array [G]: base of every rank's receive block for this request (NULL = no push)
-  long long rows_per_rank;   // entities per owner rank
+  float* const* peer_bias;   // device array [G]: every rank's receive vector of the pooled bias, or NULL
+  long long rows_per_rank;   // entities per owner rank; 0 = add every entity into ALL G ranks (all-reduce by push)
   long long stride;          // row pitch of the receive blocks, floats
-  int bias_col;              // column (float index) of the pooled bias inside the receive row, or -1
+  int G;
 };
 
 __device__ __forceinline__ void red_add_f4_sys(float* p, float4 v) {
@@ -376,8 +377,12 @@ pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const 
       }
       if (push.peer == nullptr) st_f4(out + (e0 + el) * out_stride + (size_t)col * 4, tot);
       else if (L > 0) {
-        const long long owner = (e0 + el) / push.rows_per_rank;
-        red_add_f4_sys(push.peer[owner] + ((e0 + el) - owner * push.rows_per_rank) * push.stride + (size_t)col * 4, tot);
+        if (push.rows_per_rank > 0) {
+          const long long owner = (e0 + el) / push.rows_per_rank;
+          red_add_f4_sys(push.peer[owner] + ((e0 + el) - owner * push.rows_per_rank) * push.stride + (size_t)col * 4, tot);
+        } else {
+          for (int g = 0; g < push.G; ++g) red_add_f4_sys(push.peer[g] + (e0 + el) * push.stride + (size_t)col * 4, tot);
+        }
       }
     }
     if (want_bias && tid < ne) {
@@ -389,10 +394,15 @@ pool_fwd_flat_body(const arx_attr_desc* __restrict__ g_attrs, int n_attr, const 
         else for (int w = wlo; w <= whi; ++w) bt += s_partb[w][w < whi ? 1 : 0];
       }
       if (push.peer == nullptr) bias_out[e0 + tid] = bt;                                  // :404-412
-      else if (L > 0 && push.bias_col >= 0) {
-        const long long owner = (e0 + tid) / push.rows_per_rank;
-        asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(push.peer[owner] + ((e0 + tid) - owner * push.rows_per_rank) *
-                                                                       push.stride + push.bias_col), "f"(bt) : "memory");
+      else if (L > 0 && push.peer_bias != nullptr) {
+        if (push.rows_per_rank > 0) {
+          const long long owner = (e0 + tid) / push.rows_per_rank;
+          asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(push.peer_bias[owner] + ((e0 + tid) - owner * push.rows_per_rank)),
+                       "f"(bt) : "memory");
+        } else {
+          for (int g = 0; g < push.G; ++g)
+            asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(push.peer_bias[g] + (e0 + tid)), "f"(bt) : "memory");
+        }
       }
     }
     __syncthreads();
@@ -1288,8 +1298,7 @@ static int pool_fwd_many_impl(const arx_pool_req* reqs, const arx_pool_push* pus
     const arx_pool_req& q = reqs[i];
     const bool pushed = push != nullptr && push[i].peer_out != nullptr;
     if (!q.attrs || !q.ent_ids || (!q.out && !pushed) || q.n_attr < 1 || q.n_attr > kMaxAttr || q.n < 0) return ARX_E_BADARG;
-    if (pushed && (push[i].rows_per_rank < 1 || push[i].stride < dim || (push[i].stride % 4) || push[i].bias_col >= push[i].stride))
-      return ARX_E_BADARG;
+    if (pushed && (push[i].rows_per_rank < 0 || push[i].stride < dim || (push[i].stride % 4) || push[i].n_ranks < 1)) return ARX_E_BADARG;
     if (q.n_attr > kFlatBags || q.max_rows_per_entity <= 0 || q.max_rows_per_entity > kFlatRows ||
         (!pushed && ((q.out_stride % 4) || ((uintptr_t)q.out & 15))))
       return ARX_E_UNSUPPORTED;
@@ -1310,10 +1319,10 @@ static int pool_fwd_many_impl(const arx_pool_req* reqs, const arx_pool_push* pus
     mp.n[k] = q.n; mp.out_stride[k] = q.out_stride; mp.n_attr[k] = q.n_attr; mp.epb[k] = epb;
     mp.push[k] = PushDesc{};
     if (push != nullptr && push[i].peer_out != nullptr) {
-      mp.push[k].peer = push[i].peer_out; mp.push[k].rows_per_rank = push[i].rows_per_rank;
-      mp.push[k].stride = push[i].stride; mp.push[k].bias_col = push[i].bias_col;
-      // in push mode the pooled bias goes to column bias_col of the receive row; bias_out only says "bias wanted"
-      mp.bias_out[k] = push[i].bias_col >= 0 ? reinterpret_cast<float*>(16) : nullptr;
+      mp.push[k].peer = push[i].peer_out; mp.push[k].peer_bias = push[i].peer_bias;
+      mp.push[k].rows_per_rank = push[i].rows_per_rank; mp.push[k].stride = push[i].stride; mp.push[k].G = push[i].n_ranks;
+      // in push mode the pooled bias goes to the peers' bias vectors; bias_out only says "bias wanted"
+      mp.bias_out[k] = push[i].peer_bias ? reinterpret_cast<float*>(16) : nullptr;
     }
     blocks += (int)std::min<long long>((q.n + epb - 1) / epb, slots * 4);
     mp.block_end[k] = blocks;

@@ -49,6 +49,10 @@ class RowShardExchange(object):
         return out
 
 
+class PeerUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not set the peer mapping up."""
+
+
 class _Raw(object):
     """__cuda_array_interface__ view of a device allocation that torch does not own."""
 
@@ -61,16 +65,21 @@ class PeerExchange(object):
     arx_peer_alloc allocation that all other ranks map through CUDA IPC (NVLink 5 / NVSwitch peer memory), and the
     step's own kernels write into them (csrc/peer.cu, csrc/pool.cu push mode):
 
-      loc  [mb, 2d+4]    <- red.add of partial pooled user | target vectors | target bias, from INSIDE the lookup kernel
-                            of every rank (replaces reduce-scatter and its [G*mb, 2d+4] staging buffer)
-      sp   [S, d+4]      <- red.add of every rank's partial pooled pool vectors | bias        (replaces all-reduce)
-      back [G*mb, 2d+4]  <- 128-bit stores of every rank's gradient rows dU | dPt | dts        (replaces all-gather)
-      dsp  [S, d+4]      <- red.add of every rank's partial pool gradients                    (replaces all-reduce)
+      locU [mb, d], locP [mb, d], locb [mb]   <- red.add of the partial pooled user / target vectors / target bias, from
+                                                 INSIDE the lookup kernel of every rank (lookup + reduce-scatter fused; no
+                                                 [G*mb, 2d+1] staging buffer)
+      spP [S, d], spb [S]                     <- red.add of every rank's partial pooled pool vectors / bias, from inside
+                                                 the same lookup launch (lookup + all-reduce fused)
+      ug [G*mb, d]                            <- 128-bit stores of every rank's dU rows                  (all-gather by push)
+      ig [S + G*mb, d], igb [S + G*mb]        <- the item-side gradient ARENA of the scatter-Adagrad kernel, assembled in
+                                                 place: pool rows added by every rank (all-reduce), target rows stored by
+                                                 their owners (all-gather) — no concatenation on the consumer side
 
     and two device-side barriers per step order the pushes before their consumers (arx_peer_barrier: flags in the same
-    allocation, bounded spin).  Zeroing protocol: a rank clears loc / sp after it consumed them and BEFORE it arrives at
-    the step's second barrier (the peers' next pushes come after that barrier), and clears dsp at the start of a step
-    before the first barrier.  Sums over ranks are not ordered: results can differ in the last bit for G > 2."""
+    allocation, bounded spin).  Zeroing protocol: a rank clears loc* / sp* after it consumed them and BEFORE it arrives at
+    the step's second barrier (the peers' next pushes come after that barrier), and clears the pool part of ig / igb at
+    the start of a step before the first barrier.  Sums over ranks are not ordered: results can differ in the last bit
+    for G > 2."""
 
     ALIGN = 256
 
@@ -83,56 +92,66 @@ class PeerExchange(object):
         self.device = device
         self.mb, self.S, self.d = mb, S, d
         G = self.G
-        self.W = 2 * d + 4
-        self.Wp = d + 4
-        sizes = [('loc', mb * self.W), ('sp', S * self.Wp), ('back', G * mb * self.W), ('dsp', S * self.Wp), ('flags', 64)]
+        # loc* and sp* are adjacent: ONE memset clears them
+        sizes = [('locU', mb * d), ('locP', mb * d), ('locb', mb), ('spP', S * d), ('spb', S),
+                 ('ug', G * mb * d), ('ig', (S + G * mb) * d), ('igb', S + G * mb), ('flags', 64)]
         self.off = {}
         o = 0
         for name, n in sizes:
             self.off[name] = o
             o += (n * 4 + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.nbytes = o
+        self.fwd_floats = self.off['ug'] // 4                      # locU .. spb inclusive (with alignment padding)
         lib = _lib.load()
-        base = ctypes.c_void_p()
         torch.cuda.set_device(device)
+        # every failure is agreed on COLLECTIVELY (a rank that raised alone would leave the others in a collective):
+        # stage 1 allocate + export, stage 2 map the peers; the caller falls back to the NCCL exchange on PeerUnavailable
+        base = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        why = None
         rc = lib.arx_peer_alloc(self.nbytes, ctypes.byref(base))
         if rc != 0:
-            raise RuntimeError('arx_peer_alloc(%d) failed: %d' % (self.nbytes, rc))
+            why = 'arx_peer_alloc(%d) failed: %d' % (self.nbytes, rc)
+        else:
+            rc = lib.arx_peer_export(ctypes.c_void_p(base.value), handle)
+            if rc != 0:
+                why = 'arx_peer_export failed: %d (CUDA IPC unavailable)' % rc
         self.base = base.value
-        handle = (ctypes.c_ubyte * 64)()
-        rc = lib.arx_peer_export(ctypes.c_void_p(self.base), handle)
-        if rc != 0:
-            raise RuntimeError('arx_peer_export failed: %d (CUDA IPC unavailable)' % rc)
-        handles = [None] * G
-        dist.all_gather_object(handles, bytes(handle), group=group)
+        got = [None] * G
+        dist.all_gather_object(got, (why, bytes(handle)), group=group)
+        if any(w is not None for w, _ in got):
+            if self.base:
+                lib.arx_peer_free(ctypes.c_void_p(self.base))
+            raise PeerUnavailable('; '.join('rank %d: %s' % (g, w) for g, (w, _) in enumerate(got) if w))
         self.bases = []
         for g in range(G):
             if g == self.r:
                 self.bases.append(self.base)
                 continue
             p = ctypes.c_void_p()
-            h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[g])
+            h = (ctypes.c_ubyte * 64).from_buffer_copy(got[g][1])
             rc = lib.arx_peer_open(h, ctypes.byref(p))
             if rc != 0:
-                raise RuntimeError('arx_peer_open(rank %d) failed: %d (no peer access between the GPUs?)' % (g, rc))
+                why = 'arx_peer_open(rank %d) failed: %d (no peer access between the GPUs?)' % (g, rc)
+                break
             self.bases.append(p.value)
+        got = [None] * G
+        dist.all_gather_object(got, why, group=group)
+        if any(w is not None for w in got):
+            for g, b in enumerate(self.bases):
+                if g != self.r:
+                    lib.arx_peer_close(ctypes.c_void_p(b))
+            lib.arx_peer_free(ctypes.c_void_p(self.base))
+            raise PeerUnavailable('; '.join('rank %d: %s' % (g, w) for g, w in enumerate(got) if w))
         # own blocks as torch tensors, every rank's blocks as device pointer arrays
-        self.t = {}
-        for name, n in sizes:
-            self.t[name] = torch.as_tensor(_Raw(self.base + self.off[name], n), device=device)
-        self.loc = self.t['loc'].view(mb, self.W)
-        self.sp = self.t['sp'].view(S, self.Wp)
-        self.back = self.t['back'].view(G * mb, self.W)
-        self.dsp = self.t['dsp'].view(S, self.Wp)
-
-        def ptrs(name, extra_bytes=0):
-            return torch.tensor([b + self.off[name] + extra_bytes for b in self.bases], dtype=torch.int64, device=device)
-        self.p_loc_user = ptrs('loc')
-        self.p_loc_item = ptrs('loc', 4 * d)
-        self.p_sp = ptrs('sp')
-        self.p_back = ptrs('back')
-        self.p_dsp = ptrs('dsp')
-        self.p_flags = ptrs('flags')
+        self.t = {name: torch.as_tensor(_Raw(self.base + self.off[name], n), device=device) for name, n in sizes}
+        self.fwd_all = torch.as_tensor(_Raw(self.base + self.off['locU'], self.fwd_floats), device=device)
+        self.locU, self.locP, self.locb = self.t['locU'].view(mb, d), self.t['locP'].view(mb, d), self.t['locb']
+        self.spP, self.spb = self.t['spP'].view(S, d), self.t['spb']
+        self.ug = self.t['ug'].view(G * mb, d)
+        self.ig, self.igb = self.t['ig'].view(S + G * mb, d), self.t['igb']
+        self.p = {name: torch.tensor([b + self.off[name] for b in self.bases], dtype=torch.int64, device=device)
+                  for name, _ in sizes}
         self.epoch = torch.zeros(1, dtype=torch.int32, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.timeout_ns = int(float(os.environ.get('ARX_PEER_TIMEOUT_S', '20')) * 1e9)
@@ -141,25 +160,42 @@ class PeerExchange(object):
 
     # ---- pieces of the step -----------------------------------------------------------------------------------
     def push_desc(self, which):
-        """kwargs['push'] of EmbeddingAttribute.pool_many: (device pointer array, rows per rank, row pitch, bias column)."""
+        """kwargs['push'] of EmbeddingAttribute.pool_many: (pointer array of the receive blocks, pointer array of the bias
+        vectors or None, entities per owner rank (0 = every rank gets every entity), row pitch, ranks)."""
         if which == 'user':
-            return (self.p_loc_user, self.mb, self.W, -1)
-        return (self.p_loc_item, self.mb, self.W, self.d)        # bias column 2d of the row = column d behind the item block
+            return (self.p['locU'], None, self.mb, self.d, self.G)
+        if which == 'item':
+            return (self.p['locP'], self.p['locb'], self.mb, self.d, self.G)
+        return (self.p['spP'], self.p['spb'], 0, self.d, self.G)          # 'pool'
 
     def barrier(self):
-        self._lib.call('arx_peer_barrier', self.p_flags.data_ptr(), self.r, self.G, self.epoch.data_ptr(), self.timeout_ns,
+        self._lib.call('arx_peer_barrier', self.p['flags'].data_ptr(), self.r, self.G, self.epoch.data_ptr(), self.timeout_ns,
                        self.err.data_ptr())
 
-    def add_to_all(self, src, which):
-        """src [S, d+4] partial -> += into block `which` ('sp' | 'dsp') of every rank."""
-        p = self.p_sp if which == 'sp' else self.p_dsp
-        self._lib.call('arx_peer_push_rows', src.data_ptr(), src.shape[0], src.shape[1], src.stride(0), p.data_ptr(), self.Wp, 0,
-                       self.G, -1, 1)
+    def clear_forward_blocks(self):
+        self.fwd_all.zero_()
 
-    def gather_rows(self, mine):
-        """mine [mb, 2d+4] -> rows [r*mb, (r+1)*mb) of `back` on every rank (this one included)."""
-        self._lib.call('arx_peer_push_rows', mine.data_ptr(), mine.shape[0], mine.shape[1], mine.stride(0), self.p_back.data_ptr(),
-                       self.W, self.r * self.mb, self.G, -1, 0)
+    def clear_pool_gradients(self):
+        self.ig[:self.S].zero_()
+        self.igb[:self.S].zero_()
+
+    def push_gradients(self, dU0, dPt, dts, dPs, dbs):
+        """The backward exchange in ONE launch: this rank's dU / dPt / dts rows stored into rows r*mb.. of every rank's
+        ug / ig / igb, its partial pool gradients dPs / dbs added into the pool rows of every rank's ig / igb.
+        (A vector travels as a [n/4, 4] row block.)"""
+        mb, S, d, r = self.mb, self.S, self.d, self.r
+        segs = (self._lib.PeerSeg * 5)()
+
+        def seg(k, src, dst, rows, width, src_stride, dst_stride, row0, mode):
+            q = segs[k]
+            q.src, q.dst, q.rows, q.width, q.src_stride, q.dst_stride, q.row0, q.mode = (
+                src.data_ptr(), self.p[dst].data_ptr(), rows, width, src_stride, dst_stride, row0, mode)
+        seg(0, dU0, 'ug', mb, d, dU0.stride(0), d, r * mb, 0)
+        seg(1, dPt, 'ig', mb, d, dPt.stride(0), d, S + r * mb, 0)
+        seg(2, dts, 'igb', mb // 4, 4, 4, 4, (S + r * mb) // 4, 0)
+        seg(3, dPs, 'ig', S, d, dPs.stride(0), d, 0, 1)
+        seg(4, dbs, 'igb', S // 4, 4, 4, 4, 0, 1)
+        self._lib.call('arx_peer_push_many', ctypes.addressof(segs), 5, self.G)
 
     def check(self):
         """Host-side check of the barrier watchdog (call outside the timed region)."""

@@ -6,6 +6,8 @@ partial pooled vectors are reduce-scattered so that rank r holds the complete us
 vectors of its own mb rows, scores and the loss are computed on those rows, and the gradients of
 the pooled vectors are all-gathered back so that every owner updates its rows locally.
 """
+import sys
+
 import numpy as np
 import torch
 
@@ -166,8 +168,16 @@ class ShardedLatentProductModel(LatentProductModel):
             return False
         if not (_lib.ce_supported(mb, S, d) and d % 4 == 0):
             return False
-        from .exchange import PeerExchange
-        self.px = PeerExchange(self.ex.group, self.device, mb, S, d)
+        from .exchange import PeerExchange, PeerUnavailable
+        try:
+            self.px = PeerExchange(self.ex.group, self.device, mb, S, d)
+        except PeerUnavailable as e:             # raised on every rank alike: all of them keep the NCCL collectives
+            if self._peer_pref:
+                raise
+            if self.ex.r == 0:
+                print('[arecsys_b200] peer-memory exchange unavailable, using NCCL collectives: %s' % e, file=sys.stderr)
+            self.px = None
+            return False
         return True
 
     def _step_peer(self, users_g, items_g, mb, S, masks, sync):
@@ -177,26 +187,18 @@ class ShardedLatentProductModel(LatentProductModel):
         n_g = users_g.numel()
         pre = m._out_prefix()
         f32 = dict(dtype=torch.float32, device=dev)
-        px.dsp.zero_()                                              # cleared before this step's first barrier
+        px.clear_pool_gradients()                                   # before this step's first barrier
         irng0 = m.sets[pre].attr_range()
         m.prefetch_plans({'user': [(m.sets['user'].attr_range(), users_g, POOL_MEAN)],
                           pre: [(irng0, m.sampled_ids, POOL_MEAN), (irng0, items_g, POOL_MEAN)]})
-        # lookups: partial sums of the rows this rank owns, for ALL G*mb bags, added straight into the owners' `loc`
-        # blocks (lookup + reduce-scatter in one kernel); the pool partials go to every rank's `sp` block
-        sp_part = torch.empty((S, px.Wp), **f32)
-        (_, _, urng), (_, _, irng), (ps, bs, _) = m.pool_many([
+        # ONE lookup launch: partial sums of the rows this rank owns, for ALL G*mb bags, added straight into the owners'
+        # locU / locP / locb (lookup + reduce-scatter) and, for the pool, into every rank's spP / spb (lookup + all-reduce)
+        (_, _, urng), (_, _, irng), _ = m.pool_many([
             ('user', users_g, POOL_MEAN, False, {'push': px.push_desc('user')}),
             (pre, items_g, POOL_MEAN, True, {'push': px.push_desc('item')}),
-            (pre, m.sampled_ids, POOL_MEAN, True, {'out': sp_part[:, :d]})])
-        sp_part[:, d] = bs
-        sp_part[:, d + 1:] = 0
-        px.add_to_all(sp_part, 'sp')
+            (pre, m.sampled_ids, POOL_MEAN, True, {'push': px.push_desc('pool')})])
         px.barrier()                                                # B1: every rank's pushes have landed
-        loc, sp = px.loc, px.sp
-        U0, Pt, btl = loc[:, :d], loc[:, d:2 * d], loc[:, 2 * d]
-        Ps = sp[:, :d].contiguous()
-        bsl = sp[:, d].contiguous()
-        U0 = U0.contiguous(); Pt = Pt.contiguous(); btl = btl.contiguous()
+        U0, Pt, btl, Ps, bsl = px.locU, px.locP, px.locb, px.spP, px.spb
         users_l = users_g[r * mb:(r + 1) * mb].contiguous()
         keep = self.dropout
         scale = self._scale(n_g)[:mb]                               # 1 / (G*mb): global batch mean
@@ -219,6 +221,7 @@ class ShardedLatentProductModel(LatentProductModel):
              P_r.data_ptr(), PT.data_ptr())
         if drng is not None:
             dmask = dmask_out
+        # fused_mw keeps no reference to Ps / bsl beyond its launches; they are read in place from the receive blocks
         fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l, prepared=(U_r, P_r, UT, PT))
         if fused is None:
             raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
@@ -228,26 +231,14 @@ class ShardedLatentProductModel(LatentProductModel):
         dPt = torch.empty((mb, d), **f32)
         call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), _lib.ptr(dmask), inv_keep, mb, d,
              dU0.data_ptr(), dPt.data_ptr(), _lib.ptr(drng))
-        # backward exchange: gradient rows stored into every rank's `back`, pool gradients added into every rank's `dsp`
-        mine = torch.empty((mb, px.W), **f32)
-        mine[:, :d] = dU0
-        mine[:, d:2 * d] = dPt
-        mine[:, 2 * d] = dts
-        mine[:, 2 * d + 1:] = 0
-        px.gather_rows(mine)
-        dsp_in = torch.empty((S, px.Wp), **f32)
-        dsp_in[:, :d] = dPs
-        dsp_in[:, d] = dbs
-        dsp_in[:, d + 1:] = 0
-        px.add_to_all(dsp_in, 'dsp')
-        px.loc.zero_()                                              # consumed: cleared before this step's second barrier
-        px.sp.zero_()
+        px.push_gradients(dU0, dPt, dts, dPs.contiguous(), dbs.contiguous())      # backward exchange: one launch
+        px.clear_forward_blocks()                                   # consumed: cleared before this step's second barrier
         px.barrier()                                                # B2
-        back, dsp = px.back, px.dsp
-        m.push_grad('user', urng, users_g, POOL_MEAN, back[:, :d])
+        # the receive blocks ARE the gradient arenas of the scatter-Adagrad kernels (no gather, no concatenation)
         rng = m.sets[pre].attr_range()
-        m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, dsp[:, :d].contiguous(), dsp[:, d].contiguous())
-        m.push_grad(pre, rng, items_g, POOL_MEAN, back[:, d:2 * d].contiguous(), back[:, 2 * d].contiguous())
+        m.push_grad('user', urng, users_g, POOL_MEAN, px.ug)
+        m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, px.ig[:S], px.igb[:S])
+        m.push_grad(pre, rng, items_g, POOL_MEAN, px.ig[S:], px.igb[S:])
         m.apply_gradients(self.learning_rate.eval(), OPT_ADAGRAD)
         self.global_step.assign(self.global_step.eval() + 1)
         if not sync:

@@ -91,19 +91,29 @@ int arx_pool_fwd_many(const arx_pool_req* reqs, int n_req, int dim, void* stream
  * buffers with arx_peer_alloc, exports them (CUDA IPC, 64-byte handle) and maps the other ranks' (arx_peer_open).
  * arx_pool_fwd_many_push is arx_pool_fwd_many with the PARTIAL pooled vectors of request i ADDED (red.global.add.v4.f32,
  * system scope) into the owner rank's receive block instead of stored locally: entity e belongs to rank
- * e / rows_per_rank, row e % rows_per_rank of peer_out[owner] (row pitch `stride` floats, pooled bias added to column
- * bias_col when >= 0) — lookup + reduce-scatter in one kernel; the receive blocks must be zero before the step.
+ * e / rows_per_rank, row e % rows_per_rank of peer_out[owner] (row pitch `stride` floats; the pooled bias goes to
+ * peer_bias[owner][row]) — lookup + reduce-scatter in one kernel; rows_per_rank = 0 adds every entity into ALL ranks
+ * (lookup + all-reduce); the receive blocks must be zero before the step.
  * arx_peer_push_rows copies (mode 0, rank `skip` left out) or adds (mode 1) rows into rows [row0, row0 + rows) of
  * every rank's block (all-gather / all-reduce by push).  arx_peer_barrier: device-side barrier over the G ranks
  * (flags[g] = rank g's block of >= G uint32, epoch = this rank's device counter), stream-ordered and graph-capturable;
  * a rank that waits longer than timeout_ns stores 1 + the missing rank into *err instead of spinning forever. */
 typedef struct arx_pool_push {
-  float* const* peer_out;          /* device array [G] of receive-block bases, or NULL: store to arx_pool_req.out */
-  int64_t rows_per_rank;
-  int64_t stride;
-  int32_t bias_col;
+  float* const* peer_out;          /* device array [n_ranks] of receive-block bases, or NULL: store to arx_pool_req.out */
+  float* const* peer_bias;         /* device array [n_ranks] of receive vectors for the pooled bias, or NULL           */
+  int64_t rows_per_rank;           /* entities per owner rank; 0: add every entity into ALL ranks (all-reduce by push)  */
+  int64_t stride;                  /* row pitch of the receive blocks, floats                                           */
+  int32_t n_ranks;
   int32_t reserved;
 } arx_pool_push;
+/* up to 8 row blocks pushed in one launch (arx_peer_push_many): mode 0 = store to every rank, 1 = add */
+typedef struct arx_peer_seg {
+  const float* src;                /* [rows, width], row pitch src_stride (floats, % 4) */
+  float* const* dst;               /* device array [G] of destination bases             */
+  int64_t rows, width, src_stride, dst_stride, row0;
+  int32_t mode, reserved;
+} arx_peer_seg;
+int arx_peer_push_many(const arx_peer_seg* segs, int n_segs, int G, void* stream);
 int arx_pool_fwd_many_push(const arx_pool_req* reqs, const arx_pool_push* push, int n_req, int dim, void* stream);
 int arx_peer_alloc(int64_t bytes, void** ptr);
 int arx_peer_free(void* ptr);

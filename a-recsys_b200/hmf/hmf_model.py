@@ -162,23 +162,29 @@ class LatentProductModel(object):
         """hmf_model.py:78-94.  Returns (u, ctx) where ctx lets _user_backward push dU back."""
         m = self.att_emb
         if self.nonlinear in ['relu', 'tanh']:
-            act = torch.relu if self.nonlinear == 'relu' else torch.tanh
             u0, _ = m.get_batch_user(1.0, False)                              # :87
             lookup = m._last_user
-            u0 = u0.detach().requires_grad_(True)
-
-            def drop(x, k):
-                if keep_prob == 1.0:
-                    return x
-                mk = masks[k] if masks is not None else torch.floor(torch.rand_like(x) + keep_prob)
-                return x / keep_prob * mk
-            h0 = drop(act(u0), 0)                                             # :88
-            h1 = drop(act(h0 @ self.dense['w1'] + self.dense['b1']), 1)       # :90-91
-            u = drop(act(h1 @ self.dense['w2'] + self.dense['b2']), 2)        # :93-94
+            u0, u = self._mlp_tower(u0, keep_prob, masks)
             return u.detach().contiguous(), ('mlp', lookup, u0, u)
         u, _ = m.get_batch_user(keep_prob, False, dropout_mask=masks[0] if masks else None)   # :78
         mask = getattr(m, '_last_dropout_mask', None) if keep_prob != 1.0 else None
         return u, ('linear', m._last_user, keep_prob, mask)
+
+    def _mlp_tower(self, u0, keep_prob, masks):
+        """hmf_model.py:87-94 on the pooled user vectors u0: returns (leaf, u) with u still attached to the autograd
+        graph of the dense parameters."""
+        act = torch.relu if self.nonlinear == 'relu' else torch.tanh
+        u0 = u0.detach().requires_grad_(True)
+
+        def drop(x, k):
+            if keep_prob == 1.0:
+                return x
+            mk = masks[k] if masks is not None else torch.floor(torch.rand_like(x) + keep_prob)
+            return x / keep_prob * mk
+        h0 = drop(act(u0), 0)                                                 # :88
+        h1 = drop(act(h0 @ self.dense['w1'] + self.dense['b1']), 1)           # :90-91
+        u = drop(act(h1 @ self.dense['w2'] + self.dense['b2']), 2)            # :93-94
+        return u0, u
 
     def _user_backward(self, ctx, dU):
         m = self.att_emb

@@ -24,8 +24,8 @@ class ShardedLatentProductModel(LatentProductModel):
         self.ex = RowShardExchange(group)
         kw['shard'] = (self.ex.G, self.ex.r)
         super(ShardedLatentProductModel, self).__init__(*a, **kw)
-        if self.loss_function != 'mw' or self.nonlinear in ('relu', 'tanh'):
-            raise NotImplementedError('the sharded path covers the linear HMF tower with loss mw (config 4)')
+        if self.loss_function != 'mw':
+            raise NotImplementedError('the sharded path covers HMF with loss mw (config 4)')
 
     def step(self, session, user_input, item_input, neg_item_input=None, item_sampled=None,
              item_sampled_id2idx=None, forward_only=False, recommend=False, recommend_new=False, loss=None,
@@ -33,7 +33,7 @@ class ShardedLatentProductModel(LatentProductModel):
         """user_input / item_input: the GLOBAL batch (G*mb ids, identical on every rank);
         rank r scores rows [r*mb, (r+1)*mb).  Returns the global mean loss."""
         if forward_only or recommend:
-            raise NotImplementedError('sharded evaluation / recommendation is not provided yet')
+            return self._eval_or_recommend(user_input, item_input, recommend, recommend_new)
         m, ex = self.att_emb, self.ex
         G, r, d = ex.G, ex.r, self.size
         dev = self.device
@@ -75,7 +75,8 @@ class ShardedLatentProductModel(LatentProductModel):
         users_l = users_g[r * mb:(r + 1) * mb].contiguous()
         keep = self.dropout
         scale = self._scale(n_g)[:mb]                                   # 1 / (G*mb): global batch mean
-        if _lib.ce_supported(mb, S, d) and d % 4 == 0:
+        mlp = self.nonlinear in ('relu', 'tanh')
+        if (not mlp) and _lib.ce_supported(mb, S, d) and d % 4 == 0:
             # fused glue of the single-GPU step (arx_mw_prep / arx_mw_post): dropout (mask injected, or drawn in the
             # kernel by Philox) + tf32 rounding + transposes + target score in one launch, the two adjoints in another
             f32 = dict(dtype=torch.float32, device=dev)
@@ -108,8 +109,13 @@ class ShardedLatentProductModel(LatentProductModel):
             call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), _lib.ptr(dmask), inv_keep, mb, d,
                  dU0.data_ptr(), dPt.data_ptr(), _lib.ptr(drng))
         else:
-            u = m.dropout(U0, keep, masks[0] if masks else None)
-            dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
+            if mlp:
+                # MLP tower (hmf_model.py:87-94) on this rank's rows; its dense parameters are replicated
+                u0_leaf, u_graph = self._mlp_tower(U0, keep, masks)
+                u = u_graph.detach().contiguous()
+            else:
+                u = m.dropout(U0, keep, masks[0] if masks else None)
+                dmask = getattr(m, '_last_dropout_mask', None) if keep != 1.0 else None
             tscore = torch.empty((mb,), dtype=torch.float32, device=dev)
             call('arx_rowdot_fwd', u.data_ptr(), Pt.data_ptr(), btl.data_ptr(), mb, d, tscore.data_ptr())
             fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l)
@@ -125,7 +131,22 @@ class ShardedLatentProductModel(LatentProductModel):
             loss_sum = (bl.sum() / n_g).reshape(1)
             dPt = torch.empty_like(Pt)
             call('arx_rowdot_bwd', u.data_ptr(), Pt.data_ptr(), dts.data_ptr(), mb, d, dU.data_ptr(), dPt.data_ptr())
-            if keep != 1.0:
+            if mlp:
+                for w in self.dense.values():
+                    w.grad = None
+                u_graph.backward(dU)
+                dU0 = u0_leaf.grad
+                # the ONE all-reduce of the dense parameters' gradients (every rank saw mb of the G*mb rows; the loss
+                # is already scaled by 1 / (G*mb)): identical Adagrad updates on every replica
+                names = [n for n, w in self.dense.items() if w.grad is not None]
+                flat = torch.cat([self.dense[n].grad.reshape(-1) for n in names])
+                ex.all_reduce(flat)
+                o = 0
+                for n in names:
+                    g = self.dense[n].grad
+                    g.copy_(flat[o:o + g.numel()].view_as(g))
+                    o += g.numel()
+            elif keep != 1.0:
                 dU0 = torch.empty_like(dU)
                 call('arx_scale_mask', dU.data_ptr(), dmask.data_ptr(), 1.0 / keep, dU.numel(), dU0.data_ptr())
             else:
@@ -146,12 +167,67 @@ class ShardedLatentProductModel(LatentProductModel):
         rng = m.sets[pre].attr_range()
         m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, dsp[:, :d].contiguous(), dsp[:, d].contiguous())
         m.push_grad(pre, rng, items_g, POOL_MEAN, back[:, d:2 * d].contiguous(), back[:, 2 * d].contiguous())
-        m.apply_gradients(self.learning_rate.eval(), OPT_ADAGRAD)
+        lr = self.learning_rate.eval()
+        m.apply_gradients(lr, OPT_ADAGRAD)
+        if mlp:
+            for name, w in self.dense.items():
+                if w.grad is not None:
+                    call('arx_dense_update', w.data.data_ptr(), self.dense_acc[name].data_ptr(),
+                         w.grad.contiguous().data_ptr(), w.numel(), float(lr), None, OPT_ADAGRAD)
         self.global_step.assign(self.global_step.eval() + 1)
         if not sync:
             return loss_sum
         ex.all_reduce(loss_sum)
         return float(loss_sum.item())
+
+    # ---- evaluation / recommendation on row-sharded tables (hmf_model.py:193-211) ------------------------------
+    def _catalog_full(self):
+        """Pooled catalog [V, d] + bias [V]: every rank pools the rows it owns for ALL items, one all-reduce completes
+        them; cached until the next training step (the evaluation loop calls this once per pass)."""
+        key = self.global_step.eval()
+        cache = getattr(self, '_cat_cache', None)
+        if cache is None or cache[0] != key:
+            P, beta, _ = self.att_emb.pool_catalog('full', 1)
+            self.ex.all_reduce(P)
+            self.ex.all_reduce(beta)
+            self._cat_cache = (key, P, beta)
+        return self._cat_cache[1], self._cat_cache[2]
+
+    def _eval_or_recommend(self, user_input, item_input, recommend, recommend_new):
+        """user_input / item_input: the GLOBAL batch (identical on every rank, a multiple of G rows).  The user vectors
+        are completed by an all-reduce of the per-rank partial pools, rank r scores rows [r*mb, (r+1)*mb) against the
+        full catalog, and the per-row results are gathered: recommend returns int[G*mb, top_N] on every rank, evaluation
+        the global mean of the reference's loss_eval ('warp' over the whole catalog, no positives masked: see
+        LatentProductModel.step)."""
+        if recommend and recommend_new:
+            raise AttributeError("'LatentProductModel' object has no attribute 'indices_test'")       # hmf_model.py:198
+        m, ex = self.att_emb, self.ex
+        G, r, d = ex.G, ex.r, self.size
+        m.add_input({}, user_input, item_input, forward_only=not recommend, recommend=recommend, loss='mw')
+        users_g = m.u_indices['input']
+        n_g = users_g.numel()
+        assert n_g % G == 0, 'the global batch must be a multiple of the number of ranks'
+        mb = n_g // G
+        pu, _, _ = m.pool('user', users_g, POOL_MEAN, False)               # partial sums over the rows this rank owns
+        ex.all_reduce(pu)
+        u = pu[r * mb:(r + 1) * mb].contiguous()                           # keep_prob 1.0 (:167-170, :78)
+        if self.nonlinear in ('relu', 'tanh'):
+            with torch.no_grad():
+                u = self._mlp_tower(u, 1.0, None)[1].contiguous()
+        P, beta = self._catalog_full()
+        V = P.shape[0]
+        logits = torch.empty((mb, V), dtype=torch.float32, device=self.device)
+        _lib.gemm(u, P, logits, mb, V, d, 0, 1, beta)                      # :118
+        if recommend:
+            idx = torch.empty((mb, self.top_N_items), dtype=torch.int32, device=self.device)
+            call('arx_topk_rows', logits.data_ptr(), mb, V, logits.stride(0), self.top_N_items, idx.data_ptr(), None)
+            return ex.all_gather_rows(idx).cpu().numpy()                   # :154, :200
+        items_g = m._ids(item_input)
+        targets = m.item2logit_dev[items_g[r * mb:(r + 1) * mb].long()].contiguous()
+        bl = m.compute_loss(logits, targets, 'warp', want_grad=False, forward_only=True, unmasked=True)
+        total = (bl.sum() / n_g).reshape(1)
+        ex.all_reduce(total)
+        return float(total.item())
 
     # ---- the same step over NVLink peer memory (hmf/exchange.py::PeerExchange) ---------------------------------
     def _peer_ok(self, mb, S, d):
@@ -164,7 +240,7 @@ class ShardedLatentProductModel(LatentProductModel):
         self._peer_tried = True
         import os
         want = self._peer_pref if self._peer_pref is not None else os.environ.get('ARX_PEER', '1') == '1'
-        if not self.ex.nccl or not want or self.att_emb.dim not in (128, 256):
+        if not self.ex.nccl or not want or self.att_emb.dim not in (128, 256) or self.nonlinear in ('relu', 'tanh'):
             return False
         if not (_lib.ce_supported(mb, S, d) and d % 4 == 0):
             return False

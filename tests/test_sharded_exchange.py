@@ -79,7 +79,7 @@ def test_exchange_and_sharding_arithmetic_gloo_world2():
     assert sorted(r[0] for r in res) == [0, 1] and all(all(r[1:]) for r in res), res
 
 
-def _gpu_worker(rank, world, port, q):
+def _gpu_worker(rank, world, port, q, nonlinear='linear'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'; os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
@@ -89,14 +89,19 @@ def _gpu_worker(rank, world, port, q):
     from oracle import np_oracle as O
     from helpers import positives
     ua, ia, l2i, params, dim = _setup()
+    hidden = 5
+    if nonlinear != 'linear':        # replicated MLP tower: its gradients take the one dense all-reduce of the step
+        from helpers import random_params
+        params = random_params(ua, ia, dim, 1, scale=0.4, mlp_hidden=hidden)
     l2i_d = {int(v): int(l2i[v]) for v in range(len(l2i))}
     i2l_d = {v: k for k, v in l2i_d.items()}
     mb, ns = 8, 10
     _lib.exact_fp32 = True
     model = ShardedLatentProductModel(40, 30, dim, 1, mb, 0.3, 1.0, ua, ia, i2l_d, l2i_d, loss_function='mw',
-                                      dropout=0.5, n_sampled=ns, params=params)
+                                      nonlinear=nonlinear, hidden_size=hidden,
+                                      dropout=0.5, n_sampled=ns, params={k: v.copy() for k, v in params.items()})
     emb = O.OracleEmbeddingAttribute(ua, ia, world * mb, ns, params, item_ind2logit_ind=i2l_d, logit_ind2item_ind=l2i_d)
-    om = O.OracleHMF(emb, loss='mw', keep_prob=0.5, learning_rate=0.3)
+    om = O.OracleHMF(emb, loss='mw', nonlinear=nonlinear, keep_prob=0.5, learning_rate=0.3)
     rng = np.random.default_rng(5)
     ok = True
     for it in range(3):
@@ -105,26 +110,41 @@ def _gpu_worker(rank, world, port, q):
         model.prepare_warp(pos, pos); emb.prepare_warp(pos, pos)
         sampled = [int(v) for v in rng.permutation(30)[:ns]] if it != 1 else None
         id2idx = {v: k for k, v in enumerate(sampled)} if sampled else None
-        mask = np.floor(rng.random((world * mb, dim)) + 0.5)
+        shapes = [(world * mb, dim)] if nonlinear == 'linear' else [(world * mb, dim), (world * mb, hidden), (world * mb, dim)]
+        masks = [np.floor(rng.random(sh) + 0.5) for sh in shapes]
         lg = model.step(None, users.tolist(), items.tolist(), None, sampled, id2idx, loss='mw',
-                        masks=[torch.tensor(mask[rank * mb:(rank + 1) * mb], dtype=torch.float32, device='cuda')])
-        lo = om.step(users.tolist(), items.tolist(), sampled, id2idx, masks=[mask])
+                        masks=[torch.tensor(mk[rank * mb:(rank + 1) * mb], dtype=torch.float32, device='cuda') for mk in masks])
+        lo = om.step(users.tolist(), items.tolist(), sampled, id2idx, masks=masks)
         ok = ok and abs(lg - lo) <= 1e-4 * max(1.0, abs(lo))
         for k, v in om.emb.p.items():
-            got = model.att_emb.params[k].cpu().numpy()
-            ok = ok and np.allclose(got, v[rank::world].reshape(got.shape), rtol=1e-3, atol=2e-5)
-    q.put((rank, bool(ok), lg, lo))
+            if k in model.att_emb.params:
+                got = model.att_emb.params[k].cpu().numpy()
+                ok = ok and np.allclose(got, v[rank::world].reshape(got.shape), rtol=1e-3, atol=2e-5)
+            else:                                                   # replicated dense parameter: identical on every rank
+                got = model.dense[k].detach().cpu().numpy()
+                ok = ok and np.allclose(got, v.reshape(got.shape), rtol=1e-3, atol=2e-5)
+    # evaluation loss (loss_eval) and recommendation on the sharded tables against the oracle at the global batch
+    users = rng.integers(0, 40, world * mb); items = rng.integers(0, 30, world * mb)
+    ev = model.step(None, users.tolist(), items.tolist(), forward_only=True, loss='mw')
+    eo = om.step(users.tolist(), items.tolist(), forward_only=True)
+    ok = ok and abs(ev - eo) <= 1e-4 * max(1.0, abs(eo))
+    model.top_N_items = 7
+    top = model.step(None, users.tolist(), None, recommend=True)
+    want, _ = om.top_k(users.tolist(), model.top_N_items)
+    ok = ok and top.shape == want.shape and bool((top == want).all())
+    q.put((rank, bool(ok), lg, lo, ev, eo))
     dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_sharded_hmf_matches_oracle_two_gpus():
+@pytest.mark.parametrize('nonlinear', ['linear', 'relu'])
+def test_sharded_hmf_matches_oracle_two_gpus(nonlinear):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs (run with gpurun --gpus 2)')
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q, nonlinear)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]

@@ -308,7 +308,7 @@ def mw_fwd(U_r, P_r, beta, tscore, mask, mask_ld, M, N, d):
     return hsum, loss
 
 
-def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=None, PT=None, outputs=None):
+def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=None, PT=None, outputs=None, accumulate=False):
     """(dU, dP, dbeta, dts) of sum_r g[r] * loss[r].  UT / PT: the transposed operands when the caller already has
     them (arx_mw_prep emits them with the rounding pass)."""
     dev = U_r.device
@@ -321,7 +321,7 @@ def mw_bwd(U_r, P_r, beta, tscore, mask, mask_ld, hsum, g, M, N, d, dP=None, UT=
     zeroed = 0
     if outputs is not None:                     # (dU, dP, dbeta, dts) zeroed by the caller, off the dependent chain
         dU, dP, dbeta, dts = outputs
-        zeroed = 1
+        zeroed = 2 if accumulate else 1
     else:
         dU = torch.empty((M, d), dtype=torch.float32, device=dev)
         if dP is None:

@@ -572,6 +572,149 @@ class EmbeddingAttribute(object):
             return None
         return loss, grads
 
+    # the transforms of the masked hinge sum S (embed_attribute.py:580-594): (l(S), dl/dS) as device vectors
+    @staticmethod
+    def _rs_transform(S, loss, loss_func, p):
+        lf = 'log' if loss == 'warp' else loss_func
+        if lf == 'log':
+            return torch.log1p(S), 1.0 / (1.0 + S)
+        if lf == 'exp':
+            q = torch.pow(torch.full_like(S, p), -S)
+            return 1.0 - q, float(np.log(p)) * q
+        if lf == 'poly':
+            return torch.pow(S, p), p * torch.pow(S, p - 1.0)
+        if lf == 'poly2':
+            return torch.pow(1.0 + S, p), p * torch.pow(1.0 + S, p - 1.0)
+        if lf == 'linear':
+            return S, torch.ones_like(S)
+        return S * S, 2.0 * S                                            # 'square'
+
+    def fused_warp(self, latent, targets, loss='warp', loss_func='log', exp_p=1.005, row_scale=None, want_grad=True,
+                   forward_only=False, pos_rows=None, unmasked=False, output_feat=1, max_mask_bytes=1 << 30):
+        """Full-catalog WMRB without the [rows, V] scores: get_prediction (:148-206) + _compute_warp_loss (:605-618) /
+        the hinge members of the rs family (:551-603: 'rs' with any loss_func) + their gradients, on the sampled-WMRB
+        tensor-core kernels run over the WHOLE catalog (arx_mw_fwd / arx_mw_bwd2 with N = V): the hinge sum per row comes
+        from the forward pass, its transform l(S) and l'(S) are per-row scalars applied here, and the gradient that
+        reaches the target's own score (column t of the reference's logits) is scattered back to U, P[t] and beta[t].
+        The positives of a row travel as one bit per (row, item), built per row block (<= max_mask_bytes) from the
+        per-user CSR.  Returns (loss_rows [rows], (dU, dP, dbeta) or None), or None when the shape / loss is not covered
+        (the caller then materialises the scores: arx_gemm_tc + arx_loss_rows)."""
+        if loss not in ('warp', 'rs') or output_feat not in (0, 1) or isinstance(latent, list):
+            return None
+        M, d = latent.shape[0], self.dim
+        N = self.catalog_ids.numel()
+        if not _lib.ce_supported(M, N, d):
+            return None
+        P, beta, ids = self.pool_catalog('full', output_feat)
+        U_r = _lib.round_tf32(latent if latent.is_contiguous() else latent.contiguous())
+        P_r = _lib.round_tf32(P)
+        tgt = (targets if isinstance(targets, torch.Tensor) else self._ids(targets)).long()
+        # the target's own score from the same rounded operands the kernels contract (it is one of their columns)
+        Pt_r = P_r[tgt]
+        tscore = torch.empty((M,), dtype=torch.float32, device=self.device)
+        call('arx_rowdot_fwd', U_r.data_ptr(), Pt_r.data_ptr(), beta[tgt].contiguous().data_ptr(), M, d, tscore.data_ptr())
+        pos_ptr = pos_idx = pos_row = None
+        if not unmasked:
+            pos_ptr, pos_idx = self._positives('full' + ('_eval' if forward_only else '_train'))
+            pos_row = pos_rows if pos_rows is not None else self.u_indices['input']
+        ld = _lib.mw_mask_words(N)
+        rows_per_block = max(4, min(M, (max_mask_bytes // (4 * ld)) // 4 * 4))
+        g = row_scale if row_scale is not None else torch.ones(M, dtype=torch.float32, device=self.device)
+        loss_rows = torch.empty((M,), dtype=torch.float32, device=self.device)
+        dU = dP = dbeta = None
+        if want_grad:
+            dU = torch.zeros((M, d), dtype=torch.float32, device=self.device)
+            dP = torch.zeros((N, d), dtype=torch.float32, device=self.device)
+            dbeta = torch.zeros((N,), dtype=torch.float32, device=self.device)
+            PT = torch.empty((d, N), dtype=torch.float32, device=self.device)
+            call('arx_transpose', P_r.data_ptr(), N, d, PT.data_ptr(), 0)
+        for r0 in range(0, M, rows_per_block):
+            r1 = min(M, r0 + rows_per_block)
+            n = r1 - r0
+            mask = torch.empty((n, ld), dtype=torch.int32, device=self.device)
+            if unmasked:
+                mask.zero_()
+            else:
+                call('arx_mw_mask_build', pos_row[r0:r1].contiguous().data_ptr(), pos_ptr.data_ptr(), pos_idx.data_ptr(), n, N,
+                     mask.data_ptr(), ld)
+            fw = _lib.mw_fwd(U_r[r0:r1], P_r, beta, tscore[r0:r1], mask, ld, n, N, d)
+            if fw is None:
+                return None
+            hsum, _ = fw
+            l, dl = self._rs_transform(hsum, loss, loss_func, float(exp_p))
+            loss_rows[r0:r1] = l
+            if not want_grad:
+                continue
+            # arx_mw_bwd2 scales the hinge indicator by g / (1 + hsum): hand it g * l'(S) * (1 + S)
+            gk = (g[r0:r1] * dl * (1.0 + hsum)).contiguous()
+            dts = torch.zeros((n,), dtype=torch.float32, device=self.device)
+            out = _lib.mw_bwd(U_r[r0:r1], P_r, beta, tscore[r0:r1], mask, ld, hsum, gk, n, N, d, PT=PT,
+                              outputs=(dU[r0:r1], dP, dbeta, dts), accumulate=True)     # adds into the zeroed outputs
+            if out is None:
+                return None
+            # the target column: d loss / d s_t = dts (minus the row sum of the score gradients)
+            t = tgt[r0:r1]
+            dU[r0:r1].addcmul_(dts.unsqueeze(1), P[t])
+            dP.index_add_(0, t, dts.unsqueeze(1) * latent[r0:r1])
+            dbeta.index_add_(0, t, dts)
+            del mask
+        self._last_pred = (latent, P, beta, ids, 'full', output_feat)
+        return loss_rows, ((dU, dP, dbeta) if want_grad else None)
+
+    def score_topk(self, latent, k, output_feat=1, want_lse=False, chunk=1 << 16):
+        """get_prediction (:148-206) + tf.nn.top_k(sorted=True) (hmf/hmf_model.py:154, lstm/seqModel.py:514-519) without
+        the [rows, V] scores: the catalog is scored in column blocks of `chunk` items on the tensor cores, every block
+        is reduced to its k best by arx_topk_rows, and the candidates (block order = index order) are reduced once more —
+        bit-equal to arx_topk_rows over the full matrix, ties -> lower index.  Returns (idx int32 [rows, k],
+        val [rows, k], lse [rows] or None) with lse = log sum_v exp(score) for the softmax probabilities of :515."""
+        if output_feat in (2, 3):
+            logits = self.get_prediction(latent, 'full', output_feat=output_feat)
+            P = beta = None
+            N = logits.shape[1]
+        else:
+            P, beta, _ = self.pool_catalog('full', output_feat)
+            N = P.shape[0]
+        M = latent.shape[0]
+        k = int(k)
+        lat = latent if latent.is_contiguous() else latent.contiguous()
+        n_blk = (N + chunk - 1) // chunk
+        if n_blk == 1 or k > chunk:
+            if P is not None:
+                logits = torch.empty((M, N), dtype=torch.float32, device=self.device)
+                _lib.gemm(lat, P, logits, M, N, self.dim, 0, 1, beta)
+            idx = torch.empty((M, k), dtype=torch.int32, device=self.device)
+            val = torch.empty((M, k), dtype=torch.float32, device=self.device)
+            call('arx_topk_rows', logits.data_ptr(), M, N, logits.stride(0), k, idx.data_ptr(), val.data_ptr())
+            return idx, val, (torch.logsumexp(logits, 1) if want_lse else None)
+        cand_v = torch.empty((M, n_blk * k), dtype=torch.float32, device=self.device)
+        cand_i = torch.empty((M, n_blk * k), dtype=torch.int32, device=self.device)
+        lse = torch.full((M,), float('-inf'), dtype=torch.float32, device=self.device) if want_lse else None
+        S = torch.empty((M, min(chunk, N)), dtype=torch.float32, device=self.device)
+        bi = torch.empty((M, k), dtype=torch.int32, device=self.device)
+        bv = torch.empty((M, k), dtype=torch.float32, device=self.device)
+        for b in range(n_blk):
+            c0, c1 = b * chunk, min(N, (b + 1) * chunk)
+            w = c1 - c0
+            kb = min(k, w)
+            if P is not None:
+                Sv = S.view(-1)[:M * w].view(M, w)                       # dense [M, w] block (the last one is narrower)
+                _lib.gemm(lat, P[c0:c1], Sv, M, w, self.dim, 0, 1, beta[c0:c1])
+            else:
+                Sv = logits[:, c0:c1]
+            call('arx_topk_rows', Sv.data_ptr(), M, w, Sv.stride(0), kb, bi.data_ptr(), bv.data_ptr())
+            cand_v[:, b * k:b * k + kb] = bv.view(-1)[:M * kb].view(M, kb) if kb < k else bv
+            cand_i[:, b * k:b * k + kb] = (bi.view(-1)[:M * kb].view(M, kb) if kb < k else bi) + c0
+            if kb < k:
+                cand_v[:, b * k + kb:(b + 1) * k] = float('-inf')
+                cand_i[:, b * k + kb:(b + 1) * k] = 0
+            if want_lse:
+                lse = torch.logaddexp(lse, torch.logsumexp(Sv, 1))
+        pos = torch.empty((M, k), dtype=torch.int32, device=self.device)
+        val = torch.empty((M, k), dtype=torch.float32, device=self.device)
+        call('arx_topk_rows', cand_v.data_ptr(), M, n_blk * k, cand_v.stride(0), k, pos.data_ptr(), val.data_ptr())
+        idx = torch.gather(cand_i, 1, pos.long())
+        return idx.contiguous(), val, lse
+
     # -- embed_attribute.py:208-220 --------------------------------------------------------
     def get_target_score(self, latent, inds, device='/gpu:0'):
         ids = self._ids(inds)

@@ -626,6 +626,8 @@ extern "C" int arx_mw_bwd(const float* U, const float* P, const float* UT, const
 
 // outputs_zeroed != 0: the caller has already zeroed dU, dP, dbeta and dts (e.g. with one memset at the top of the step,
 // off the dependent chain): the split accumulation then starts without the four memsets in front of the kernels.
+// outputs_zeroed == 2: ALWAYS add into the outputs (also when one split covers a tile): row blocks of a large batch
+// accumulate their dP / dbeta into the same buffers (full-catalog WMRB, embed_attribute.py::fused_warp).
 extern "C" int arx_mw_bwd2(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                            const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
                            int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts,
@@ -646,7 +648,7 @@ extern "C" int arx_mw_bwd2(const float* U, const float* P, const float* UT, cons
     const int tps = ce_split(row_tiles, (N + CE_BN - 1) / CE_BN, &nsplit);
     CeParams p{};
     p.R = M; p.S = N; p.d = (int)d; p.tiles_per_split = tps; p.beta = beta; p.lse = hsum; p.g = g; p.ts = tscore;
-    p.mask = mask; p.mask_ld = mask_ld; p.out = dU; p.dts = dts; p.atomic_out = nsplit > 1;
+    p.mask = mask; p.mask_ld = mask_ld; p.out = dU; p.dts = dts; p.atomic_out = nsplit > 1 || outputs_zeroed == 2;
     if (p.atomic_out && !outputs_zeroed) {
       if (cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)M * d, st) != cudaSuccess) return ARX_E_LAUNCH;
       if (cudaMemsetAsync(dts, 0, sizeof(float) * (size_t)M, st) != cudaSuccess) return ARX_E_LAUNCH;
@@ -660,7 +662,7 @@ extern "C" int arx_mw_bwd2(const float* U, const float* P, const float* UT, cons
     const int tps = ce_split(row_tiles, (M + CE_BN - 1) / CE_BN, &nsplit);
     CeParams p{};
     p.R = N; p.S = M; p.d = (int)d; p.tiles_per_split = tps; p.beta = beta; p.lse = hsum; p.g = g; p.ts = tscore;
-    p.mask = mask; p.mask_ld = mask_ld; p.out = dP; p.dbeta = dbeta; p.atomic_out = nsplit > 1;
+    p.mask = mask; p.mask_ld = mask_ld; p.out = dP; p.dbeta = dbeta; p.atomic_out = nsplit > 1 || outputs_zeroed == 2;
     if (p.atomic_out && !outputs_zeroed) {
       if (cudaMemsetAsync(dP, 0, sizeof(float) * (size_t)N * d, st) != cudaSuccess) return ARX_E_LAUNCH;
       if (dbeta && cudaMemsetAsync(dbeta, 0, sizeof(float) * (size_t)N, st) != cudaSuccess) return ARX_E_LAUNCH;

@@ -236,10 +236,8 @@ class LatentProductModel(object):
             if recommend_new:
                 raise AttributeError("'LatentProductModel' object has no attribute 'indices_test'")  # :198
             u, _ = self._user_tower(1.0, None)
-            logits = m.get_prediction(u)
-            idx = torch.empty((mb, self.top_N_items), dtype=torch.int32, device=self.device)
-            call('arx_topk_rows', logits.data_ptr(), mb, logits.shape[1], logits.stride(0), self.top_N_items,
-                 idx.data_ptr(), None)
+            # scoring + top-k in column blocks of the catalog: the [mb, V] scores are never held at once
+            idx, _, _ = m.score_topk(u, self.top_N_items)
             return idx.cpu().numpy()                                           # :154,:200
 
         item_ids = m._ids(item_input)
@@ -412,6 +410,11 @@ class LatentProductModel(object):
         else:
             u, ctx = self._user_tower(keep_prob, masks)
             fused = m.fused_ce(u, targets, scale, train) if eff == 'ce' else None
+            if fused is None and eff in ('warp', 'rs'):
+                # full-catalog WMRB on the same tensor-core pipeline (embed_attribute.py:551-618): hinge sums and their
+                # adjoints without the [mb, V] scores
+                fused = m.fused_warp(u, targets, eff, self.loss_func, self.loss_exp_p, scale, train,
+                                     forward_only=forward_only, unmasked=unmasked)
             if fused is not None:
                 # full-catalog scoring fused with the softmax CE on the tensor cores: the [mb, V]
                 # logits (16 GB at C2) are never written (:118 + embed_attribute.py:530)

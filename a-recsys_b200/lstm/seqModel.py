@@ -223,6 +223,10 @@ class SeqModel(object):
         pool = 'sampled' if eff == 'mw' else 'full'
         nonlinear = self.output_feat in (2, 3)      # max / log-sum-exp pooling of the token scores: literal order (K3m)
         fused = m.fused_ce(Hf, tgt, row_scale, train, pool, self.output_feat) if (eff == 'ce' and not nonlinear) else None
+        if fused is None and eff in ('warp', 'rs') and not nonlinear:
+            # full-catalog WMRB of all T*mb positions without the [T*mb, V] scores (embed_attribute.py:551-618)
+            fused = m.fused_warp(Hf, tgt, eff, 'log', 1.005, row_scale, train, forward_only=forward_only,
+                                 pos_rows=users.repeat(T).contiguous(), output_feat=self.output_feat)
         if fused is not None:
             # all T*mb positions scored against the catalog and reduced to the softmax CE on the tensor
             # cores without materialising [T*mb, V] logits (seqModel.py:480-493 + sequence_loss)
@@ -336,19 +340,19 @@ class SeqModel(object):
         Hout = self.cell.forward(X, 1.0)
         pos = torch.as_tensor(np.asarray(positions, dtype=np.int64)).to(self.device)
         hsel = Hout[pos, torch.arange(mb, device=self.device)].contiguous()            # [mb, H]
-        if self.output_feat in (2, 3):
-            # one get_prediction per time step, as the reference's graph has it (the output_feat 3 pooling depends on
-            # the maximum token score of the step's whole batch); every sequence keeps the row of its last position
-            N = m.catalog_ids.numel()
-            S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
-            for t in sorted(set(int(p) for p in positions)):
-                sel = (pos == t).nonzero().reshape(-1)
-                S[sel] = m.get_prediction(Hout[t].contiguous(), 'full', output_feat=self.output_feat)[sel]
-        else:
-            P, beta, _ = m.pool_catalog('full', self.output_feat)
-            N = P.shape[0]
-            S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
-            _lib.gemm(hsel, P, S, mb, N, self.size, 0, 1, beta)
+        if self.output_feat not in (2, 3):
+            # scoring + top-k in column blocks of the catalog, softmax denominator accumulated alongside (:514-519)
+            idx, val, lse = m.score_topk(hsel, self.topk_n, self.output_feat, want_lse=True)
+            prob = torch.exp(val - lse.unsqueeze(1))
+            idx, prob = idx.cpu().numpy(), prob.cpu().numpy()
+            return [(user_input[i], prob[i, :], idx[i, :]) for i in range(mb)]
+        # output_feat 2 / 3: one get_prediction per time step, as the reference's graph has it (the output_feat 3 pooling
+        # depends on the maximum token score of the step's whole batch); every sequence keeps the row of its last position
+        N = m.catalog_ids.numel()
+        S = torch.empty((mb, N), dtype=torch.float32, device=self.device)
+        for t in sorted(set(int(p) for p in positions)):
+            sel = (pos == t).nonzero().reshape(-1)
+            S[sel] = m.get_prediction(Hout[t].contiguous(), 'full', output_feat=self.output_feat)[sel]
         idx = torch.empty((mb, self.topk_n), dtype=torch.int32, device=self.device)
         val = torch.empty((mb, self.topk_n), dtype=torch.float32, device=self.device)
         call('arx_topk_rows', S.data_ptr(), mb, N, S.stride(0), self.topk_n, idx.data_ptr(), val.data_ptr())

@@ -94,10 +94,7 @@ class Model(object):
         if recommend:
             if recommend_new:
                 raise AttributeError("'Model' object has no attribute 'indices_test'")       # linear_seq.py:96
-            logits = m.get_prediction(h, output_feat=self.output_feat)
-            idx = torch.empty((mb, self.top_N_items), dtype=torch.int32, device=self.device)
-            call('arx_topk_rows', logits.data_ptr(), mb, logits.shape[1], logits.stride(0), self.top_N_items,
-                 idx.data_ptr(), None)
+            idx, _, _ = m.score_topk(h, self.top_N_items, self.output_feat)      # column blocks: no [mb, V] scores
             return idx.cpu().numpy()
         out_ids = m._ids(item_output)
         targets = m.item2logit_dev[out_ids.long()].contiguous()
@@ -123,7 +120,10 @@ class Model(object):
             P = Ps
         else:
             fused = m.fused_ce(h, targets, scale, train, 'full', self.output_feat) if eff == 'ce' else None
-            if fused is not None:        # scoring + softmax CE + adjoints on the tensor cores, no [mb, V] logits
+            if fused is None and eff in ('warp', 'rs'):                          # full-catalog WMRB, same pipeline
+                fused = m.fused_warp(h, targets, eff, 'log', 1.005, scale, train, forward_only=forward_only,
+                                     output_feat=self.output_feat)
+            if fused is not None:        # scoring + softmax CE / WMRB + adjoints on the tensor cores, no [mb, V] logits
                 batch_loss, fgrads = fused
             else:
                 logits = m.get_prediction(h, output_feat=self.output_feat)

@@ -317,7 +317,8 @@ int arx_mw_fwd(const float* U, const float* P, const float* beta, const float* t
 int arx_mw_bwd(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
                int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, void* stream);
-/* Same, with outputs_zeroed != 0 when the caller has zeroed dU, dP, dbeta and dts itself (off the dependent chain). */
+/* Same, with outputs_zeroed != 0 when the caller has zeroed dU, dP, dbeta and dts itself (off the dependent chain);
+ * 2 = always ADD into them (row blocks of one batch accumulating into shared dP / dbeta: full-catalog WMRB). */
 int arx_mw_bwd2(const float* U, const float* P, const float* UT, const float* PT, const float* beta,
                 const float* tscore, const uint32_t* mask, int64_t mask_ld, const float* hsum, const float* g,
                 int64_t M, int64_t N, int64_t d, float* dU, float* dP, float* dbeta, float* dts, int outputs_zeroed,

@@ -106,6 +106,8 @@ SIGNATURES = {
     'arx_peer_barrier': [vp, i32, i32, vp, i64, vp, vp],
     'arx_peer_push_rows': [vp, i64, i64, i64, vp, i64, i64, i32, i32, i32, vp],
     'arx_peer_push_many': [vp, i32, i32, vp],
+    'arx_bwd_plan_alloc_h': [vp, BwdPlan, i32, vp],
+    'arx_pool_bwd_apply_slab': [vp, i32, i32, BwdPlan, vp, i32, vp, f32, vp, i32, i32, vp],
     'arx_score_max': [vp, vp, i64, i64, vp, vp],
     'arx_token_pool_fwd': [vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp],
     'arx_token_pool_bwd': [vp, vp, vp, i64, vp, vp, i64, i32, vp, f32, vp, vp, vp, vp, vp],

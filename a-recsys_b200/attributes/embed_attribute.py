@@ -193,6 +193,7 @@ class EmbeddingAttribute(object):
         self.sampled_ids = None
         self.sampled_pos_dev = None
         self.dense_table_grads = {}     # prefix -> {variable name: dense gradient}  (output_feat 2 / 3 scoring)
+        self.deterministic = os.environ.get('ARX_DETERMINISTIC', '0') == '1'     # canonical bucket order (see _canonical_buckets)
         self.pos_csr = {}          # (kind) -> (ptr, idx) per-user positives, device
         self.pos_item_set = None
         self.pos_item_set_eval = None
@@ -914,13 +915,15 @@ class EmbeddingAttribute(object):
                 ev.record(side)
             ts._prefetched = (plan, self._plan_sig(specs), ev)
 
-    def _build_plan(self, ts, specs, single_key):
+    def _build_plan(self, ts, specs, single_key, heavy=None):
         cap_occ = 0
         for (a0, na, ids, mode) in specs:
             cap_occ += int(ids.numel()) * sum(ts.max_len[a0:a0 + na])
-        if single_key == 'catalog':
+        if single_key is not None and single_key.startswith('catalog'):
             ia = self.item_attributes     # exact: the catalog CSR is static
-            cap_occ = int(specs[0][2].numel()) * ts.n_cat + sum(len(v) for v in ia.full_values_tr)
+            a0, na = specs[0][0], specs[0][1]
+            cap_occ = sum(int(specs[0][2].numel()) if a < ts.n_cat else len(ia.full_values_tr[a - ts.n_cat])
+                          for a in range(a0, a0 + na))
         cap_occ = max(cap_occ, 1)
         cap_rows = max(min(cap_occ, ts.total_vocab), 1)
         plan = _Plan(self.device, cap_rows, cap_occ, self.dim) if single_key is not None else self._scratch_plan(ts, cap_rows, cap_occ)
@@ -939,15 +942,42 @@ class EmbeddingAttribute(object):
         call('arx_bwd_plan_begin', plan.c)
         for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_count', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), plan.c)
-        call('arx_bwd_plan_alloc', ts.desc_ptr(0), plan.c)
+        if heavy is None:
+            call('arx_bwd_plan_alloc', ts.desc_ptr(0), plan.c)
+        else:                                               # explicit chunk size (the column-slab apply repeats it)
+            call('arx_bwd_plan_alloc_h', ts.desc_ptr(0), plan.c, int(heavy))
         row = 0
         for (a0, na, ids, mode) in specs:
             call('arx_bwd_plan_fill', ts.desc_ptr(0), a0, na, ids.data_ptr(), ids.numel(), mode, row, plan.c)
             row += ids.numel() * (na if mode == POOL_CONCAT else 1)
         call('arx_bwd_plan_end', ts.desc_ptr(0), plan.c)
+        if self.deterministic:
+            self._canonical_buckets(plan)
         if single_key is not None:
             ts.plans[single_key] = plan
         return plan
+
+    @staticmethod
+    def _canonical_buckets(plan):
+        """Deterministic scatter mode: arx_bwd_plan_fill places the contributions of a table row into its
+        bucket in the order its atomics happen to retire, so the fp32 sum of a row's gradient can differ in the last bit
+        from run to run.  Here every bucket is put into ascending order of the contributing arena row (ties carry equal
+        weights), which fixes the summation order of arx_pool_bwd_apply — also for hot rows, whose chunks are consecutive
+        slices of the bucket folded in chunk order.  Needs the counters on the host: eager steps only (a debugging and
+        regression-test mode; capture_step refuses it)."""
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError('deterministic scatter mode reads the plan counters on the host: not capturable')
+        nu, occ = int(plan.counters[0].item()), int(plan.counters[1].item())
+        if nu == 0 or occ == 0:
+            return
+        base = plan.row_base[:nu].long()
+        cnt = plan.row_cnt[:nu].long()
+        order = torch.argsort(base)
+        seg = torch.repeat_interleave(torch.arange(nu, device=base.device), cnt[order])      # bucket index by position
+        key = seg * (1 << 31) + plan.bucket_src[:occ].long()
+        perm = torch.argsort(key)
+        plan.bucket_src[:occ] = plan.bucket_src[:occ][perm]
+        plan.bucket_w[:occ] = plan.bucket_w[:occ][perm]
 
     def _scratch_plan(self, ts, cap_rows, cap_occ):
         p = getattr(ts, '_scratch', None)
@@ -1103,19 +1133,58 @@ class EmbeddingAttribute(object):
                 forks.append(side)
             with torch.cuda.stream(side if side is not None else main):
                 ready = getattr(ts, '_ready', None)
+                _lib.tag = ts.prefix
+                if ready is None and self._apply_catalog_slabs(ts, lr, grad_scale, opt):
+                    ts.pending = []                      # gradient of the whole pooled catalog: column-slab passes
+                    continue
                 if ready is not None:
                     plan, arena, bias = ready
                     ts._ready = None
                 else:
                     plan = self._plan_for(ts, ts.pending)
                     arena, bias = self._arena(ts.pending)
-                _lib.tag = ts.prefix
                 call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, plan.c, arena.data_ptr(),
                      arena.stride(0), ptr(bias), float(lr), ptr(grad_scale), opt, None, None)
             ts.pending = []
         for side in forks:
             main.wait_stream(side)
         self._after_apply()
+
+    CATALOG_SLAB_HEAVY = 512
+
+    def _apply_catalog_slabs(self, ts, lr, grad_scale, opt):
+        """The gradient of the WHOLE pooled catalog (loss = ce / full-catalog WMRB: push_grad(..., plan_key='catalog') as
+        the only pending lookup of its table set) in column slabs of 16 floats (arx_pool_bwd_apply_slab): the slab-major
+        copy of dP is L2-resident, so the ~100 gathers per table row hit L2 instead of DRAM.  The id table (one
+        contribution per row: pure streaming) keeps the row-at-a-time kernel on its own static plan.  Returns False when
+        the case is not this one (the caller then runs the general kernel)."""
+        if len(ts.pending) != 1 or os.environ.get('ARX_CATALOG_SLABS', '1') != '1':
+            return False
+        a0, na, ids, mode, dout, dbias, key = ts.pending[0]
+        if (key != 'catalog' or mode != POOL_MEAN or self.dim % 16 != 0 or self.shard is not None or na < 2 or a0 != 0
+                or ts.n_cat != 1 or opt not in (OPT_ADAGRAD, OPT_SGD) or not dout.is_contiguous()
+                or dout.numel() * 4 < (32 << 20) or self.deterministic):
+            return False
+        V = ids.numel()
+        plans = getattr(ts, '_slab_plans', None)
+        if plans is None:
+            # static plans: id table | attribute tables; the mean over the F = na attributes of the LOOKUP stays in the
+            # weights (the sub-plans were filled with 1 / their own attribute count)
+            p_id = self._build_plan(ts, [(0, 1, ids, mode)], 'catalog_id')
+            p_at = self._build_plan(ts, [(1, na - 1, ids, mode)], 'catalog_attr', heavy=self.CATALOG_SLAB_HEAVY)
+            p_id.bucket_w[:int(p_id.counters[1].item())] *= 1.0 / na
+            p_at.bucket_w[:int(p_at.counters[1].item())] *= (na - 1.0) / na
+            plans = ts._slab_plans = (p_id, p_at)
+        p_id, p_at = plans
+        lr = float(lr)
+        call('arx_pool_bwd_apply', ts.desc_ptr(0), ts.n_attr, self.dim, p_id.c, dout.data_ptr(), dout.stride(0), ptr(dbias),
+             lr, ptr(grad_scale), opt, None, None)
+        ns = self.dim // 16
+        slabs = dout.view(V, ns, 16).permute(1, 0, 2).contiguous()                 # [ns][V][16]: 64 B per item and slab
+        for s_ in range(ns):
+            call('arx_pool_bwd_apply_slab', ts.desc_ptr(0), ts.n_attr, self.dim, p_at.c, slabs[s_].data_ptr(), 16 * s_,
+                 ptr(dbias), lr, ptr(grad_scale), opt, self.CATALOG_SLAB_HEAVY)
+        return True
 
     def _after_apply(self):
         # A plan that ran out of capacity makes plan_fill / apply return without touching anything: surface it instead

@@ -1098,6 +1098,154 @@ pool_bwd_apply_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int
   pool_bwd_apply_body<VEC, FLAT>(s_attrs, dim, plan, dout, dout_stride, dbias, lr, grad_scale_dev, opt, rows_out, bias_rows_out, heavy);
 }
 
+// ---- column-slab apply for the catalog gradient (loss = ce / full-catalog WMRB) ---------------------------------
+// The gradient of the pooled catalog, dP [V, d], reaches every table row through ~100 contributions (10^6 items x 97
+// rows each at C2: 97 M gathers of 512 B over a 512 MB arena, 4x the L2) — the row-at-a-time kernel above is bound by
+// those DRAM gathers.  Adagrad is element-wise, so the update can be done one COLUMN SLAB at a time: the caller lays
+// dP out slab-major ([d / 16][V][16], 64 MB per slab at V = 10^6: L2-resident), and pass s updates columns
+// [16 s, 16 s + 16) of every touched row from gathers that hit L2; the table / accumulator rows are touched 64 B at a
+// time, once per pass.  Lanes: 8 entry slots x 4 float4 columns — one warp instruction gathers 8 contributions of 64 B.
+// Rows above `heavy` contributions are split into chunks that different warps reduce (the plan's chunk list, built by
+// arx_bwd_plan_alloc_h with the same `heavy`); the last chunk to arrive folds the partials in chunk order and updates.
+__device__ __forceinline__ float4 slab_reduce_slots(float4 a) {
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    a.x += __shfl_xor_sync(ARX_FULL_MASK, a.x, o); a.y += __shfl_xor_sync(ARX_FULL_MASK, a.y, o);
+    a.z += __shfl_xor_sync(ARX_FULL_MASK, a.z, o); a.w += __shfl_xor_sync(ARX_FULL_MASK, a.w, o);
+  }
+  return a;
+}
+
+// sum over bucket entries [base, base + cnt) of w * dslab[src][4 cl .. 4 cl + 4), reduced over the 8 entry slots (every
+// lane of column cl returns the total); gb = sum of w * dbias[src] (warp total) when dbias != NULL
+__device__ __forceinline__ float4 slab_bucket(const arx_bwd_plan& plan, int base, int cnt, const float* __restrict__ dslab,
+                                              int lane, const float* __restrict__ dbias, float& gb) {
+  const int slot = lane >> 2, cl = lane & 3;
+  float4 acc = f4_zero();
+  float gbl = 0.f;
+  for (int e0 = 0; e0 < cnt; e0 += 32) {
+    int s_l = -1; float w_l = 0.f;
+    if (e0 + lane < cnt) {
+      s_l = __ldg(plan.bucket_src + base + e0 + lane); w_l = __ldg(plan.bucket_w + base + e0 + lane);
+      if (dbias != nullptr) gbl = fmaf(w_l, __ldg(dbias + s_l), gbl);
+    }
+    float4 v[4]; float wj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sj = __shfl_sync(ARX_FULL_MASK, s_l, j * 8 + slot);
+      wj[j] = __shfl_sync(ARX_FULL_MASK, w_l, j * 8 + slot);
+      v[j] = sj >= 0 ? ldg_f4(dslab + (size_t)sj * 16 + cl * 4) : f4_zero();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) f4_fma(acc, wj[j], v[j]);
+  }
+  gb = dbias != nullptr ? warp_sum(gbl) : 0.f;
+  return slab_reduce_slots(acc);
+}
+
+__device__ __forceinline__ void slab_row_update(const arx_attr_desc& a, size_t off, float4 g, float lr, int opt) {
+  float* wp = a.table + off;
+  float4 wv = ld_f4(wp);
+  if (opt == ARX_OPT_ADAGRAD) {
+    float* ap = a.table_acc + off;
+    float4 av = ld_f4(ap);
+    V<4>::adagrad(wv, av, g, lr);
+    st_f4(ap, av);
+  } else {
+    V<4>::sgd(wv, g, lr);
+  }
+  st_f4(wp, wv);
+}
+
+__global__ void __launch_bounds__(256, 4)
+pool_bwd_apply_slab_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr, int dim, arx_bwd_plan plan,
+                           const float* __restrict__ dslab, int c0, const float* __restrict__ dbias, float lr,
+                           const float* __restrict__ grad_scale_dev, int opt, int heavy) {
+  __shared__ arx_attr_desc s_attrs[kMaxAttr];
+  stage_descs(s_attrs, g_attrs, n_attr);
+  if (plan.counters[2] != 0) return;
+  const int lane = threadIdx.x & 31, slot = lane >> 2, cl = lane & 3;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nu = (int)min((long long)plan.counters[0], (long long)plan.cap_rows);
+  const int nchunks = (int)min((long long)plan.counters[4], (long long)plan.cap_chunks);
+  const float gs = grad_scale_dev ? __ldg(grad_scale_dev) : 1.0f;
+  const float* __restrict__ db = (c0 == 0) ? dbias : nullptr;           // the bias column rides with the first slab
+  float* __restrict__ part = plan.partials;                             // [cap_chunks][16]
+  float* __restrict__ part_b = plan.partials + (size_t)plan.cap_chunks * dim;
+
+  // ---- hot rows: one chunk per warp iteration -------------------------------------------------------------------
+  for (long long ch = warp0; ch < nchunks; ch += nwarps) {
+    const int u = plan.chunk_row[ch];
+    const int cb = plan.row_chunk0[u];
+    const int k = (int)ch - cb;
+    const int rc = plan.row_cnt[u];
+    const int nch = (rc + heavy - 1) / heavy;
+    float gb;
+    const float4 g = slab_bucket(plan, plan.row_base[u] + k * heavy, min(heavy, rc - k * heavy), dslab, lane, db, gb);
+    if (slot == 0) st_f4(part + (size_t)ch * 16 + cl * 4, g);
+    if (lane == 0 && db != nullptr) part_b[ch] = gb;
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicAdd(&plan.row_done[u], 1) == nch - 1) ? 1 : 0;
+    last = __shfl_sync(ARX_FULL_MASK, last, 0);
+    if (!last) continue;
+    __threadfence();
+    const int f = plan.uniq_attr[u];
+    const int tok = local_row(shard_of(s_attrs[f]), plan.uniq_tok[u]);
+    float4 tot = f4_zero();
+    float tb = 0.f;
+    for (int k0 = 0; k0 < nch; k0 += 8) {                 // chunk k0 + slot: fixed order per slot, then a fixed tree
+      if (k0 + slot < nch) f4_add(tot, V<4>::ldcg(part + (size_t)(cb + k0 + slot) * 16 + cl * 4));
+    }
+    tot = slab_reduce_slots(tot);
+    if (db != nullptr && s_attrs[f].bias != nullptr) {
+      for (int kk = lane; kk < nch; kk += 32) tb += __ldcg(part_b + cb + kk);
+      tb = warp_sum(tb);
+    }
+    if (slot == 0) slab_row_update(s_attrs[f], (size_t)tok * dim + c0 + cl * 4, f4_scale(tot, gs), lr, opt);
+    if (lane == 0) {
+      if (db != nullptr && s_attrs[f].bias != nullptr) bias_update(s_attrs[f], tok, tb * gs, lr, opt);
+      plan.row_done[u] = 0;
+    }
+  }
+
+  // ---- all other rows: 32 per warp iteration (strided over the unique list), one after the other --------------
+  const int n_iter = (nu + 31) >> 5;
+  for (long long it = warp0; it < n_iter; it += nwarps) {
+    const int u = lane * n_iter + (int)it;
+    int tok = 0, f = 0, base = 0, cnt = 0;
+    if (u < nu) {
+      f = __ldg(plan.uniq_attr + u);
+      tok = local_row(shard_of(s_attrs[f]), __ldg(plan.uniq_tok + u));
+      base = __ldg(plan.row_base + u); cnt = __ldg(plan.row_cnt + u);
+    }
+    const unsigned lightmask = __ballot_sync(ARX_FULL_MASK, (u < nu) && (cnt <= heavy));
+    for (int r = 0; r < 32; ++r) {
+      if (!((lightmask >> r) & 1u)) continue;
+      const int fr = __shfl_sync(ARX_FULL_MASK, f, r), tr = __shfl_sync(ARX_FULL_MASK, tok, r);
+      const int br = __shfl_sync(ARX_FULL_MASK, base, r), cr = __shfl_sync(ARX_FULL_MASK, cnt, r);
+      // the row's table / accumulator slab is requested before the bucket walk (independent of it)
+      const size_t off = (size_t)tr * dim + c0 + cl * 4;
+      float4 wv = f4_zero(), av = f4_zero();
+      if (slot == 0) {
+        wv = ld_f4(s_attrs[fr].table + off);
+        if (opt == ARX_OPT_ADAGRAD) av = ld_f4(s_attrs[fr].table_acc + off);
+      }
+      const bool hb = db != nullptr && s_attrs[fr].bias != nullptr;
+      float gb;
+      float4 g = slab_bucket(plan, br, cr, dslab, lane, hb ? db : nullptr, gb);
+      g = f4_scale(g, gs);
+      if (slot == 0) {
+        if (opt == ARX_OPT_ADAGRAD) { V<4>::adagrad(wv, av, g, lr); st_f4(s_attrs[fr].table_acc + off, av); }
+        else V<4>::sgd(wv, g, lr);
+        st_f4(s_attrs[fr].table + off, wv);
+      }
+      if (lane == 0 && hb) bias_update(s_attrs[fr], tr, gb * gs, lr, opt);
+    }
+  }
+}
+
 // Several table sets (the user and the item tables of one training step) in ONE launch: a warp that has run out of rows
 // of the first set goes straight on to the second — one launch ramp and one tail instead of two.
 struct ApplySet {
@@ -1398,6 +1546,30 @@ extern "C" int arx_bwd_plan_count(const arx_attr_desc* attrs, int attr_begin, in
 extern "C" int arx_bwd_plan_alloc(const arx_attr_desc* attrs, arx_bwd_plan plan, void* stream) {
   if (!attrs || !plan_args_ok(plan)) return ARX_E_BADARG;
   plan_alloc_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(attrs, plan, g_tune_heavy);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+// arx_bwd_plan_alloc with an explicit chunk size (the plan and the kernel that applies it must agree on it)
+extern "C" int arx_bwd_plan_alloc_h(const arx_attr_desc* attrs, arx_bwd_plan plan, int heavy, void* stream) {
+  if (!attrs || !plan_args_ok(plan) || heavy < 8 || heavy > 4096) return ARX_E_BADARG;
+  plan_alloc_kernel<<<arx_num_sms() * 4, 256, 0, (cudaStream_t)stream>>>(attrs, plan, heavy);
+  ARX_CHECK_LAUNCH();
+  return ARX_OK;
+}
+
+// One column slab of the de-duplicated optimizer step: dslab [rows of the gradient arena][16] = columns [c0, c0 + 16)
+// of dOut (slab-major copy made by the caller), dim % 16 == 0, ARX_OPT_ADAGRAD / ARX_OPT_SGD.  dbias is applied by
+// the pass with c0 == 0.  heavy: the chunk size the plan was allocated with (arx_bwd_plan_alloc_h).
+extern "C" int arx_pool_bwd_apply_slab(const arx_attr_desc* attrs, int n_attr, int dim, arx_bwd_plan plan, const float* dslab,
+                                       int c0, const float* dbias, float lr, const float* grad_scale_dev, int opt, int heavy,
+                                       void* stream) {
+  if (!attrs || !dslab || n_attr < 1 || n_attr > kMaxAttr || dim < 16 || (dim % 16) || c0 < 0 || c0 + 16 > dim || (c0 % 16) ||
+      !plan_args_ok(plan) || heavy < 8 || heavy > 4096 || (((uintptr_t)dslab) & 15))
+    return ARX_E_BADARG;
+  if (opt != ARX_OPT_ADAGRAD && opt != ARX_OPT_SGD) return ARX_E_UNSUPPORTED;
+  pool_bwd_apply_slab_kernel<<<arx_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(attrs, n_attr, dim, plan, dslab, c0, dbias, lr,
+                                                                                grad_scale_dev, opt, heavy);
   ARX_CHECK_LAUNCH();
   return ARX_OK;
 }

@@ -435,17 +435,40 @@ def main():
                          'peak': peak, 'unit': 'GB/s', 'frac': step_bytes / (ms_step * 1e-3) / 1e9 / peak,
                          'what': 'embedding fwd+bwd bytes of both sides (unique rows) / ms_per_step', 'peak_source': peak_src}
     dom = max(roofs, key=lambda k: per_kernel[k]['ms_per_step']) if roofs else None
+    ku, ki = 'arx_pool_bwd_apply:user', 'arx_pool_bwd_apply:item'
+    if ku in roofs and ki in roofs:
+        # the dominant KERNEL is pool_bwd_apply_kernel<4>: two launches per step (user tables, item tables).  Its
+        # roofline entry is what the contract defines — algorithmic bytes per launch / the kernel's average launch
+        # duration, over BOTH launches; the per-side entries stay in roofline_all.
+        ru, ri = roofs[ku], roofs[ki]
+        us = 0.5 * (ru['avg_us'] + ri['avg_us'])
+        nb_u = 0.5 * (ru['algorithmic_bytes'] + ri['algorithmic_bytes'])
+        nb_n = 0.5 * (ru['algorithmic_bytes_nominal'] + ri['algorithmic_bytes_nominal'])
+        key = 'arx_pool_bwd_apply:both'
+        roofs[key] = {'bound': 'hbm', 'achieved': nb_u / us / 1e3, 'peak': peak, 'unit': 'GB/s', 'frac': nb_u / us / 1e3 / peak,
+                      'traffic': None, 'achieved_nominal': nb_n / us / 1e3, 'algorithmic_bytes': nb_u,
+                      'algorithmic_bytes_nominal': nb_n, 'avg_us': us, 'launches_per_step': 2,
+                      'kernel': 'pool_bwd_apply_kernel<4>: average over its two launches per step (user tables: %.1f us, '
+                                'frac %.3f; item tables (pool + targets): %.1f us, frac %.3f)'
+                                % (ru['avg_us'], ru['frac'], ri['avg_us'], ri['frac']), 'peak_source': peak_src}
+        dom = key
     tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'traffic.json')
     # dram bytes per launch from the committed ncu --set full capture (profiles/r1_ncu_summary.md; the first
     # launch of each kernel in the eager step is the user side)
     tkeys = {'arx_pool_fwd:user': 'void pool_fwd_flat_kernel<1> grid %d #1' % ((a.mb + 6) // 7),
-             'arx_pool_bwd_apply:user': 'void pool_bwd_apply_kernel<4> grid 592 #1'}
+             'arx_pool_bwd_apply:user': 'void pool_bwd_apply_kernel<4> grid 592 #1',
+             'arx_pool_bwd_apply:item': 'void pool_bwd_apply_kernel<4> grid 592 #2',
+             'arx_pool_fwd_many:many': 'void pool_fwd_flat_many_kernel<1> grid 1319 #1'}
     if os.path.exists(tpath):
+        tj = json.load(open(tpath))
         for k, r in roofs.items():
-            t = json.load(open(tpath)).get(tkeys.get(k, ''))
+            t = tj.get(tkeys.get(k, ''))
             if t:
                 r['traffic'] = t['dram_bytes_read'] + t['dram_bytes_write']
                 r['traffic_source'] = t['source']
+        if 'arx_pool_bwd_apply:both' in roofs and roofs[ku].get('traffic') and roofs[ki].get('traffic'):
+            roofs['arx_pool_bwd_apply:both']['traffic'] = 0.5 * (roofs[ku]['traffic'] + roofs[ki]['traffic'])
+            roofs['arx_pool_bwd_apply:both']['traffic_source'] = roofs[ki].get('traffic_source')
 
     out = {'metric': 'interactions/sec', 'value': value, 'unit': 'interactions/s', 'n_gpus': world,
            'steps': a.steps, 'warmup': a.warmup, 'ms_per_step': ms_step, 'higher_is_better': True,

@@ -194,7 +194,18 @@ int arx_pool_bwd_apply(const arx_attr_desc* attrs, int n_attr, int dim,
 typedef struct arx_apply_set {
   const arx_attr_desc* attrs;      /* all descriptors of the table set */
   const float* dout;               /* gradient arena [R, dout_stride] */
-  const float* dbias;              /* [R] bias-gradient arena or NULL */
+  const float* dbias;              /* Column-slab variant for the gradient of the WHOLE pooled catalog (loss = ce / full-catalog WMRB: every item
+ * contributes, ~100 contributions per table row, a 512 MB arena at C2).  Adagrad is element-wise, so the step is done
+ * 16 columns at a time: dslab = columns [c0, c0 + 16) of the arena laid out contiguously ([rows][16], slab-major copy made
+ * by the caller: L2-resident), every pass gathers from L2 and touches 64 B of each table / accumulator row.  The plan is
+ * allocated with an explicit chunk size (arx_bwd_plan_alloc_h instead of arx_bwd_plan_alloc) that the apply calls repeat.
+ * dbias is consumed by the pass with c0 == 0.  Same semantics as arx_pool_bwd_apply (hmf/hmf_model.py:146-151). */
+int arx_bwd_plan_alloc_h(const arx_attr_desc* attrs, arx_bwd_plan plan, int heavy, void* stream);
+int arx_pool_bwd_apply_slab(const arx_attr_desc* attrs, int n_attr, int dim, arx_bwd_plan plan, const float* dslab,
+                            int c0, const float* dbias, float lr, const float* grad_scale_dev, int opt, int heavy,
+                            void* stream);
+
+/* [R] bias-gradient arena or NULL */
   int64_t dout_stride;
   arx_bwd_plan plan;
   int32_t n_attr;

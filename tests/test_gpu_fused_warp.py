@@ -124,3 +124,36 @@ def test_blocked_score_topk_keeps_tie_order(cuda):
     call('arx_topk_rows', logits.data_ptr(), logits.shape[0], logits.shape[1], logits.stride(0), k, idx_w.data_ptr(), None)
     idx, _, _ = emb.score_topk(latent, k, chunk=512)
     assert torch.equal(idx, idx_w)
+
+
+@pytest.mark.parametrize('opt_name', ['adagrad', 'sgd'])
+def test_catalog_gradient_in_column_slabs_equals_the_row_kernel(cuda, opt_name, monkeypatch):
+    """arx_pool_bwd_apply_slab (+ arx_bwd_plan_alloc_h): the de-duplicated optimizer step for the gradient of the whole
+    pooled catalog, 16 columns at a time from an L2-resident slab, against the row-at-a-time kernel on the same dP —
+    hot rows (chunked), rows with one contribution (id table), biases, and a clip scale."""
+    from arecsys_b200 import _lib
+    from arecsys_b200._lib import POOL_MEAN, OPT_ADAGRAD, OPT_SGD
+    from arecsys_b200.attributes.embed_attribute import EmbeddingAttribute
+    dim, ni = 128, 70000
+    ua, ia, i2l, l2i = small_dataset(50, ni, 3, 3000, 6, 12, 1, None, dim)
+    params = random_params(ua, ia, dim, 2, scale=0.3)
+    rng = np.random.default_rng(0)
+    dP = torch.tensor(rng.standard_normal((ni, dim)).astype(np.float32) * 1e-2, device=cuda)
+    db = torch.tensor(rng.standard_normal(ni).astype(np.float32) * 1e-2, device=cuda)
+    scale = torch.tensor([0.37], dtype=torch.float32, device=cuda)
+    opt = OPT_ADAGRAD if opt_name == 'adagrad' else OPT_SGD
+    out = {}
+    for slabs in ('0', '1'):
+        monkeypatch.setenv('ARX_CATALOG_SLABS', slabs)
+        emb = EmbeddingAttribute(ua, ia, 16, None, 0, False, i2l, l2i, params={k: v.copy() for k, v in params.items()})
+        pre = emb._out_prefix()
+        for _ in range(2):                                   # twice: the accumulators of the first step feed the second
+            emb.push_grad(pre, emb.sets[pre].attr_range(), emb.catalog_ids, POOL_MEAN, dP, db, plan_key='catalog')
+            emb.apply_gradients(0.3, opt, grad_scale=scale)
+        emb.check_plans()
+        assert (getattr(emb.sets[pre], '_slab_plans', None) is not None) == (slabs == '1')
+        out[slabs] = {k: v.clone() for k, v in emb.params.items() if k.startswith('item')}
+        out[slabs].update({'acc/' + k: v.clone() for k, v in emb.accs.items() if k.startswith('item')})
+    for k in out['0']:
+        a, b = out['0'][k], out['1'][k]
+        assert float((a - b).abs().max()) <= 2e-5 * max(1.0, float(a.abs().max())), k

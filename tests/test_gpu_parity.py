@@ -155,6 +155,35 @@ def test_pool_bwd_row_gradients_match_oracle(cuda, dim, mode):
         assert int(t.abs().sum().item()) == 0
 
 
+def test_deterministic_scatter_mode_fixes_the_bucket_order(cuda):
+    """EmbeddingAttribute.deterministic (ARX_DETERMINISTIC=1): every bucket of the backward plan is put into ascending
+    order of the contributing arena row, so the de-duplicated row gradients (hot rows with thousands of contributions
+    included) are bit-identical from run to run, and still equal to the default mode within fp32 rounding."""
+    model, om, ua, ia = _build(128)
+    m = model.att_emb
+    rng = np.random.default_rng(3)
+    ids = rng.integers(0, 8, 6000)                   # 6000 lookups over 8 items: every row is hot (chunked) or heavy
+    d = torch.tensor(rng.standard_normal((6000, 128)).astype(np.float32), device='cuda')
+    b = torch.tensor(rng.standard_normal(6000).astype(np.float32), device='cuda')
+    rngA = m.sets['item'].attr_range()
+    runs = []
+    for det in (True, True, True, False):
+        m.deterministic = det
+        m.push_grad('item', rngA, m._ids(ids), 0, d, b)
+        runs.append({k: v.clone() for k, v in m.row_gradients('item').items()})
+        if det:
+            plan = m.sets['item']._scratch                 # the plan row_gradients just built (buckets stay in place)
+            nu, occ = int(plan.counters[0].item()), int(plan.counters[1].item())
+            base, cnt = plan.row_base[:nu].cpu().numpy(), plan.row_cnt[:nu].cpu().numpy()
+            src = plan.bucket_src[:occ].cpu().numpy()
+            assert cnt.max() > 64                          # hot rows present
+            assert all(np.all(np.diff(src[b0:b0 + c]) >= 0) for b0, c in zip(base, cnt))
+    m.deterministic = False
+    for k in runs[0]:
+        assert torch.equal(runs[0][k], runs[1][k]) and torch.equal(runs[0][k], runs[2][k]), k
+        assert torch.allclose(runs[0][k], runs[3][k], rtol=1e-4, atol=1e-4), k
+
+
 @pytest.mark.parametrize('shape', [(5, 7, 3), (64, 64, 16), (130, 77, 33), (16, 300, 128)])
 def test_gemm_variants(cuda, shape):
     from arecsys_b200._lib import call

@@ -1,17 +1,14 @@
-run() {
-  env "$@" python bench.py --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/r2_sw.json 2> gpurun_out/r2_sw.err
-  python - "$*" <<PY
+python -m pytest tests/test_gpu_fused_warp.py tests/test_gpu_parity.py -x -q -m gpu -k "slabs or deterministic" 2>&1 | tail -15
+for sl in 1 0; do
+  ARX_CATALOG_SLABS=$sl timeout 400 python bench.py --loss ce --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ce_slab$sl.json 2> gpurun_out/r2_ce_slab$sl.err
+  python - $sl <<PY
 import json,sys
+sl=sys.argv[1]
 try:
-    d=json.loads(open("gpurun_out/r2_sw.json").read().strip().splitlines()[-1])
-    print(sys.argv[1], round(d["value"]), round(d["ms_per_step"],4), {k.replace('arx_',''):round(v["avg_us"],1) for k,v in d["per_kernel"].items() if "apply" in k or "plan" in k or "fwd_many" in k})
+    d=json.loads([l for l in open("gpurun_out/r2_ce_slab%s.json"%sl).read().strip().splitlines() if l.startswith('{')][-1])
+    print('slabs', sl, round(d["value"]), round(d["ms_per_step"],3), 'loss', d["e2e"].get("last_loss"))
+    print({k.replace('arx_',''):(round(v["ms_per_step"],3), v["launches_per_step"]) for k,v in d["per_kernel"].items() if v["ms_per_step"]>0.2})
 except Exception as e:
-    print(sys.argv[1], 'FAILED', e); print(open("gpurun_out/r2_sw.err").read()[-800:])
+    print('FAILED', e); print(open("gpurun_out/r2_ce_slab%s.err"%sl).read()[-1500:])
 PY
-}
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_shapes.py -x -q -m gpu 2>&1 | tail -4
-run A=1
-run ARX_TUNE=apply_flat=1
-run ARX_TUNE=apply_ctas_per_sm=2
-run ARX_TUNE=apply_ctas_per_sm=6
-run ARX_TUNE=apply_contig=1
+done

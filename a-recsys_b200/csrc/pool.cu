@@ -1126,7 +1126,9 @@ __device__ __forceinline__ float4 slab_bucket(const arx_bwd_plan& plan, int base
   for (int e0 = 0; e0 < cnt; e0 += 32) {
     int s_l = -1; float w_l = 0.f;
     if (e0 + lane < cnt) {
-      s_l = __ldg(plan.bucket_src + base + e0 + lane); w_l = __ldg(plan.bucket_w + base + e0 + lane);
+      // the bucket arrays are streamed once per pass (0.8 GB at C2): evict-first, so that they do not push the slab
+      // (the only data with reuse) out of L2
+      s_l = __ldcs(plan.bucket_src + base + e0 + lane); w_l = __ldcs(plan.bucket_w + base + e0 + lane);
       if (dbias != nullptr) gbl = fmaf(w_l, __ldg(dbias + s_l), gbl);
     }
     float4 v[4]; float wj[4];
@@ -1143,18 +1145,22 @@ __device__ __forceinline__ float4 slab_bucket(const arx_bwd_plan& plan, int base
   return slab_reduce_slots(acc);
 }
 
+// table / accumulator slabs are touched once per pass: streaming (evict-first) loads and stores
+__device__ __forceinline__ float4 ldcs_f4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stcs_f4(float* p, float4 v) { __stcs(reinterpret_cast<float4*>(p), v); }
+
 __device__ __forceinline__ void slab_row_update(const arx_attr_desc& a, size_t off, float4 g, float lr, int opt) {
   float* wp = a.table + off;
-  float4 wv = ld_f4(wp);
+  float4 wv = ldcs_f4(wp);
   if (opt == ARX_OPT_ADAGRAD) {
     float* ap = a.table_acc + off;
-    float4 av = ld_f4(ap);
+    float4 av = ldcs_f4(ap);
     V<4>::adagrad(wv, av, g, lr);
-    st_f4(ap, av);
+    stcs_f4(ap, av);
   } else {
     V<4>::sgd(wv, g, lr);
   }
-  st_f4(wp, wv);
+  stcs_f4(wp, wv);
 }
 
 __global__ void __launch_bounds__(256, 4)
@@ -1229,17 +1235,17 @@ pool_bwd_apply_slab_kernel(const arx_attr_desc* __restrict__ g_attrs, int n_attr
       const size_t off = (size_t)tr * dim + c0 + cl * 4;
       float4 wv = f4_zero(), av = f4_zero();
       if (slot == 0) {
-        wv = ld_f4(s_attrs[fr].table + off);
-        if (opt == ARX_OPT_ADAGRAD) av = ld_f4(s_attrs[fr].table_acc + off);
+        wv = ldcs_f4(s_attrs[fr].table + off);
+        if (opt == ARX_OPT_ADAGRAD) av = ldcs_f4(s_attrs[fr].table_acc + off);
       }
       const bool hb = db != nullptr && s_attrs[fr].bias != nullptr;
       float gb;
       float4 g = slab_bucket(plan, br, cr, dslab, lane, hb ? db : nullptr, gb);
       g = f4_scale(g, gs);
       if (slot == 0) {
-        if (opt == ARX_OPT_ADAGRAD) { V<4>::adagrad(wv, av, g, lr); st_f4(s_attrs[fr].table_acc + off, av); }
+        if (opt == ARX_OPT_ADAGRAD) { V<4>::adagrad(wv, av, g, lr); stcs_f4(s_attrs[fr].table_acc + off, av); }
         else V<4>::sgd(wv, g, lr);
-        st_f4(s_attrs[fr].table + off, wv);
+        stcs_f4(s_attrs[fr].table + off, wv);
       }
       if (lane == 0 && hb) bias_update(s_attrs[fr], tr, gb * gs, lr, opt);
     }

@@ -1,7 +1,6 @@
 n=${1:-2}
-timeout -k 10 300 python -m pytest tests/test_sharded_exchange.py -x -q -m gpu 2>&1 | tail -15
-for peer in 1; do
-  ARX_PEER=$peer timeout -k 10 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$peer bench.py --gpus $n --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r2_mg_n${n}_peer$peer.json 2> gpurun_out/r2_mg_n${n}_peer$peer.err
+for peer in ${2:-1}; do
+  ARX_PEER=$peer timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$peer bench.py --gpus $n --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r2_mg_n${n}_peer$peer.json 2> gpurun_out/r2_mg_n${n}_peer$peer.err
   echo "rc=$? peer=$peer"
   python - $n $peer <<PY
 import json,sys

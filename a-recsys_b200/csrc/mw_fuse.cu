@@ -44,6 +44,67 @@ mw_prep_kernel(const float* __restrict__ u0, const float* __restrict__ mask, flo
   float* __restrict__ dst_r = is_u ? U_r : P_r;
   float* __restrict__ dst_t = is_u ? UT : PT;
   const int ld = d + 1;
+  if ((d & 3) == 0) {
+    // 128-bit path: a lane owns 4 consecutive columns (one Philox block = the same 4 mask values the scalar path
+    // draws), the warp's 4 rows are loaded together (all loads of the tile in flight before the first use)
+    const int d4 = d >> 2;
+    constexpr int RPW = kPrepRows / 8;
+    float dot[RPW];
+#pragma unroll
+    for (int q = 0; q < RPW; ++q) dot[q] = 0.f;
+    const int n_it = (d4 + 31) >> 5;                      // uniform trip count: the warp reductions below need every lane
+    for (int itc = 0; itc < n_it; ++itc) {
+      const int c4 = itc * 32 + lane;
+      const bool cok = c4 < d4;
+      float4 x[RPW], pt[RPW], mk[RPW];
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const long long row = row0 + warp + 8 * q;
+        x[q] = f4_zero(); pt[q] = f4_zero(); mk[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (cok && row < R) {
+          x[q] = ldg_f4(src + row * d + c4 * 4);
+          if (is_u && mask != nullptr) mk[q] = ldg_f4(mask + row * d + c4 * 4);
+          if (is_u && Pt != nullptr) pt[q] = ldg_f4(Pt + row * d + c4 * 4);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const int r = warp + 8 * q;
+        const long long row = row0 + r;
+        if (!cok) continue;
+        float4 v = x[q];
+        if (row < R) {
+          if (is_u) {
+            if (mask != nullptr) {
+              v = make_float4(v.x * inv_keep * mk[q].x, v.y * inv_keep * mk[q].y, v.z * inv_keep * mk[q].z, v.w * inv_keep * mk[q].w);
+            } else if (rng != nullptr) {
+              uint32_t o[4];
+              philox_words(rng, (unsigned long long)(row * d + c4 * 4) >> 2, o);
+              const float keep = 1.0f / inv_keep;
+              const float4 m = make_float4(floorf(keep + u01(o[0])), floorf(keep + u01(o[1])), floorf(keep + u01(o[2])),
+                                           floorf(keep + u01(o[3])));
+              st_f4(mask_out + row * d + c4 * 4, m);
+              v = make_float4(v.x * inv_keep * m.x, v.y * inv_keep * m.y, v.z * inv_keep * m.z, v.w * inv_keep * m.w);
+            }
+            st_f4(u + row * d + c4 * 4, v);
+            dot[q] = fmaf(v.x, pt[q].x, fmaf(v.y, pt[q].y, fmaf(v.z, pt[q].z, fmaf(v.w, pt[q].w, dot[q]))));
+          }
+          v = make_float4(tf32_round(v.x), tf32_round(v.y), tf32_round(v.z), tf32_round(v.w));
+          st_f4(dst_r + row * d + c4 * 4, v);
+        }
+        float* t = tile + r * ld + c4 * 4;
+        t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+      }
+    }
+    if (is_u && tscore != nullptr) {
+#pragma unroll
+      for (int q = 0; q < RPW; ++q) {
+        const long long row = row0 + warp + 8 * q;
+        const float dsum = warp_sum(dot[q]);
+        if (lane == 0 && row < R) tscore[row] = dsum + (bt != nullptr ? __ldg(bt + row) : 0.f);   // :220
+      }
+    }
+  } else
   for (int r = warp; r < kPrepRows; r += 8) {
     const long long row = row0 + r;
     float dot = 0.f;

@@ -1,8 +1,7 @@
-python -m pytest tests/test_gpu_fused_warp.py -x -q -m gpu -k "slabs" 2>&1 | tail -3
-timeout 400 python bench.py --loss ce --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2_ce_slab2.json 2> gpurun_out/r2_ce_slab2.err
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_bench_shapes.py tests/test_ref_golden.py -x -q -m gpu -k "mw or glue or hmf" 2>&1 | tail -4
+python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/r2_sw.json 2> gpurun_out/r2_sw.err
 python - <<PY
 import json
-d=json.loads([l for l in open("gpurun_out/r2_ce_slab2.json").read().strip().splitlines() if l.startswith('{')][-1])
-print(round(d["value"]), round(d["ms_per_step"],3), {k.replace('arx_',''):(round(v["ms_per_step"],3), v["launches_per_step"]) for k,v in d["per_kernel"].items() if v["ms_per_step"]>0.2})
+d=json.loads(open("gpurun_out/r2_sw.json").read().strip().splitlines()[-1])
+print(round(d["value"]), round(d["ms_per_step"],4), 'e2e', round(d['e2e']['value']), {k.replace('arx_',''):round(v["avg_us"],1) for k,v in d["per_kernel"].items()})
 PY
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,lts__t_sector_hit_rate.pct --clock-control none -k regex:pool_bwd_apply_slab -s 8 -c 2 python bench.py --loss ce --steps 1 --warmup 1 --no-cpu-baseline --no-graph 2>&1 | grep -E "gpu__time|dram__bytes|hit_rate"

@@ -45,6 +45,7 @@ class _Saver(object):
         m = self.model
         if global_step is not None:
             path = '%s-%d' % (path, global_step)
+        logical = path
         path = self._shard_path(path)
         state = {'params': {k: v.cpu() for k, v in m.att_emb.params.items()},
                  'accs': {k: v.cpu() for k, v in m.att_emb.accs.items()},
@@ -52,16 +53,21 @@ class _Saver(object):
                  'dense_acc': {k: v.cpu() for k, v in m.dense_acc.items()},
                  'learning_rate': m.learning_rate.eval(), 'global_step': m.global_step.eval()}
         torch.save(state, path)
+        # the index names the LOGICAL checkpoint: every rank of a sharded run writes the same line and finds its own
+        # shard file from it on restore
         with open(os.path.join(os.path.dirname(path), 'checkpoint'), 'w') as f:
-            f.write('model_checkpoint_path: "%s"\n' % os.path.basename(path))
+            f.write('model_checkpoint_path: "%s"\n' % os.path.basename(logical))
         return path
 
     def _shard_path(self, path):
         """Row-sharded tables: every rank owns different rows, so each writes / reads its own file."""
         sh = self.model.att_emb.shard
-        if sh is not None and '.shard' not in os.path.basename(path):
-            path = '%s.shard%dof%d' % (path, sh[1], sh[0])
-        return path
+        d, b = os.path.dirname(path), os.path.basename(path)
+        if '.shard' in b:
+            b = b[:b.index('.shard')]                      # a path that names another rank's file: take the logical name
+        if sh is not None:
+            b = '%s.shard%dof%d' % (b, sh[1], sh[0])
+        return os.path.join(d, b)
 
     def restore(self, sess, path):
         m = self.model

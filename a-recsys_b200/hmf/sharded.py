@@ -33,7 +33,7 @@ class ShardedLatentProductModel(LatentProductModel):
         """user_input / item_input: the GLOBAL batch (G*mb ids, identical on every rank);
         rank r scores rows [r*mb, (r+1)*mb).  Returns the global mean loss."""
         if forward_only or recommend:
-            return self._eval_or_recommend(user_input, item_input, recommend, recommend_new)
+            return self._eval_or_recommend(user_input, item_input, recommend, recommend_new, loss)
         m, ex = self.att_emb, self.ex
         G, r, d = ex.G, ex.r, self.size
         dev = self.device
@@ -193,7 +193,7 @@ class ShardedLatentProductModel(LatentProductModel):
             self._cat_cache = (key, P, beta)
         return self._cat_cache[1], self._cat_cache[2]
 
-    def _eval_or_recommend(self, user_input, item_input, recommend, recommend_new):
+    def _eval_or_recommend(self, user_input, item_input, recommend, recommend_new, loss=None):
         """user_input / item_input: the GLOBAL batch (identical on every rank, a multiple of G rows).  The user vectors
         are completed by an all-reduce of the per-rank partial pools, rank r scores rows [r*mb, (r+1)*mb) against the
         full catalog, and the per-row results are gathered: recommend returns int[G*mb, top_N] on every rank, evaluation
@@ -224,7 +224,16 @@ class ShardedLatentProductModel(LatentProductModel):
             return ex.all_gather_rows(idx).cpu().numpy()                   # :154, :200
         items_g = m._ids(item_input)
         targets = m.item2logit_dev[items_g[r * mb:(r + 1) * mb].long()].contiguous()
-        bl = m.compute_loss(logits, targets, 'warp', want_grad=False, forward_only=True, unmasked=True)
+        # as LatentProductModel.step: the model's own sampled loss evaluates as the full-catalog 'warp' with NO positives
+        # masked (the reference's quirk, hmf_model.py:209-211); an explicit loss (the runner passes 'warp') masks the
+        # evaluation positives of each row's user
+        eff = loss if loss is not None else self.loss_function
+        unmasked = eff == 'mw'
+        if eff == 'mw':
+            eff = 'warp'
+        users_l = users_g[r * mb:(r + 1) * mb].contiguous()
+        bl = m.compute_loss(logits, targets, eff, loss_func=self.loss_func, exp_p=self.loss_exp_p, want_grad=False,
+                            forward_only=True, unmasked=unmasked, pos_rows=users_l)
         total = (bl.sum() / n_g).reshape(1)
         ex.all_reduce(total)
         return float(total.item())

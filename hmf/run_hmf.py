@@ -68,7 +68,45 @@ FLAGS.DEFINE_string("model_option", 'loss', "model to evaluation")
 FLAGS.DEFINE_integer("max_steps", 0, "stop after this many steps (0 = n_epoch decides)")
 
 
+# Not in the reference (single GPU): launched under torchrun (WORLD_SIZE > 1), the tables are row-sharded over the ranks
+# (arecsys_b200.hmf.sharded.ShardedLatentProductModel).  Every rank runs this same script with the same seeds,
+# so all of them assemble the same GLOBAL batches (--batch_size is the global batch) and draw the same negative pools;
+# rank r scores rows [r * mb, (r + 1) * mb) of each batch.  Only rank 0 logs.
+WORLD = int(os.environ.get('WORLD_SIZE', '1'))
+RANK = int(os.environ.get('RANK', '0'))
+
+
+def _dist_setup():
+    if WORLD == 1:
+        return
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if FLAGS.batch_size % WORLD:
+        raise SystemExit('--batch_size is the GLOBAL batch: it must be a multiple of the %d ranks' % WORLD)
+    if FLAGS.loss != 'mw':
+        raise SystemExit('row-sharded training covers --loss mw (SURVEY 8e); got %r' % FLAGS.loss)
+
+
+def _rank0_first(fn):
+    """Run fn on rank 0 first (it writes the attribute-store cache), then on the other ranks (they read it)."""
+    if WORLD == 1:
+        return fn()
+    import torch.distributed as dist
+    out = fn() if RANK == 0 else None
+    dist.barrier()
+    if RANK != 0:
+        out = fn()
+    dist.barrier()
+    return out
+
+
 def mylog(msg):
+    if RANK != 0:
+        return
     print(msg)
     logging.info(msg)
 
@@ -80,7 +118,11 @@ def create_model(session, u_attributes=None, i_attributes=None, item_ind2logit_i
     loss = FLAGS.loss if loss is None else loss
     gpu = None if FLAGS.gpu == -1 else FLAGS.gpu
     n_sampled = FLAGS.n_sampled if FLAGS.loss in ['mw', 'mce'] else None
-    model = hmf_model.LatentProductModel(
+    cls = hmf_model.LatentProductModel
+    if WORLD > 1:
+        from arecsys_b200.hmf.sharded import ShardedLatentProductModel as cls
+        gpu = int(os.environ.get('LOCAL_RANK', '0'))
+    model = cls(
         FLAGS.user_vocab_size, FLAGS.item_vocab_size, FLAGS.size, FLAGS.num_layers, FLAGS.batch_size,
         FLAGS.learning_rate, FLAGS.learning_rate_decay_factor, u_attributes, i_attributes,
         item_ind2logit_ind, logit_ind2item_ind, loss_function=loss, GPU=gpu,
@@ -88,8 +130,7 @@ def create_model(session, u_attributes=None, i_attributes=None, item_ind2logit_i
         n_sampled=n_sampled, indices_item=ind_item, top_N_items=FLAGS.top_N_items,
         hidden_size=FLAGS.hidden_size, loss_func=FLAGS.loss_func, loss_exp_p=FLAGS.loss_exp_p,
         seed=FLAGS.seed)
-    if not os.path.isdir(FLAGS.train_dir):
-        os.mkdir(FLAGS.train_dir)
+    os.makedirs(FLAGS.train_dir, exist_ok=True)
     ckpt = os.path.join(FLAGS.train_dir, 'checkpoint')
     if os.path.isfile(ckpt):
         name = open(ckpt).read().split('"')[1]
@@ -112,11 +153,11 @@ def train():
         steps_per_checkpoint = 30                                             # :146
     sess = None
     mylog("reading data")
-    (data_tr, data_va, u_attributes, i_attributes, item_ind2logit_ind, logit_ind2item_ind, _, _) = read_data(
+    (data_tr, data_va, u_attributes, i_attributes, item_ind2logit_ind, logit_ind2item_ind, _, _) = _rank0_first(lambda: read_data(
         raw_data_dir=raw_data, data_dir=data_dir, combine_att=FLAGS.combine_att,
         logits_size_tr=FLAGS.item_vocab_size, thresh=FLAGS.item_vocab_min_thresh,
         use_user_feature=FLAGS.use_user_feature, use_item_feature=FLAGS.use_item_feature,
-        test=FLAGS.test, mylog=mylog)
+        test=FLAGS.test, mylog=mylog))
     mylog("train/dev size: %d/%d" % (len(data_tr), len(data_va)))
     # remove rare items from both sets (run_hmf.py:163-171)
     mylog("original train/dev size: %d/%d" % (len(data_tr), len(data_va)))
@@ -264,11 +305,11 @@ def recommend(target_uids=[]):
     from arecsys_b200.attributes.input_attribute import read_data
     batch_size, top_n = FLAGS.batch_size, FLAGS.top_N_items
     mylog("reading data")
-    (_, _, u_attributes, i_attributes, item_ind2logit_ind, logit_ind2item_ind, user_index, item_index) = read_data(
+    (_, _, u_attributes, i_attributes, item_ind2logit_ind, logit_ind2item_ind, user_index, item_index) = _rank0_first(lambda: read_data(
         raw_data_dir=FLAGS.raw_data, data_dir=FLAGS.data_dir, combine_att=FLAGS.combine_att,
         logits_size_tr=FLAGS.item_vocab_size, thresh=FLAGS.item_vocab_min_thresh,
         use_user_feature=FLAGS.use_user_feature, use_item_feature=FLAGS.use_item_feature,
-        test=FLAGS.test, mylog=mylog)
+        test=FLAGS.test, mylog=mylog))
     model = create_model(None, u_attributes, i_attributes, item_ind2logit_ind, logit_ind2item_ind,
                          loss=FLAGS.loss, ind_item=None)
     Uinds = [user_index[v] for v in target_uids]
@@ -301,8 +342,10 @@ def recommend(target_uids=[]):
 def compute_scores():
     """run_hmf.py:411-427."""
     from arecsys_b200.utils.evaluate import Evaluation
-    evaluation = Evaluation(FLAGS.raw_data, test=FLAGS.test)
+    evaluation = _rank0_first(lambda: Evaluation(FLAGS.raw_data, test=FLAGS.test))   # writes historical_*.csv once
     R = recommend(evaluation.get_uids())
+    if RANK != 0:
+        return                                                # every rank holds the same top-N lists; rank 0 scores them
     evaluation.eval_on(R)
     scores_self, scores_ex = evaluation.get_scores()
     mylog("====evaluation scores (NDCG, RECALL, PRECISION, MAP) @ 2,5,10,20,30====")
@@ -315,15 +358,22 @@ def main(_=None):
     if FLAGS.test:
         FLAGS.data_dir = (FLAGS.data_dir[:-1] if FLAGS.data_dir[-1] == '/' else FLAGS.data_dir) + '_test'
     if not os.path.exists(FLAGS.train_dir):
-        os.makedirs(FLAGS.train_dir)
+        os.makedirs(FLAGS.train_dir, exist_ok=True)
+    _dist_setup()
     if not FLAGS.recommend:
-        print('train')
-        logging.basicConfig(filename=os.path.join(FLAGS.train_dir, "log.txt"), level=logging.DEBUG)
+        if RANK == 0:
+            print('train')
+            logging.basicConfig(filename=os.path.join(FLAGS.train_dir, "log.txt"), level=logging.DEBUG)
         train()
     else:
-        print('recommend')
-        logging.basicConfig(filename=os.path.join(FLAGS.train_dir, "log.recommend.txt"), level=logging.DEBUG)
+        if RANK == 0:
+            print('recommend')
+            logging.basicConfig(filename=os.path.join(FLAGS.train_dir, "log.recommend.txt"), level=logging.DEBUG)
         compute_scores()
+    if WORLD > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -965,7 +965,7 @@ class EmbeddingAttribute(object):
         weights), which fixes the summation order of arx_pool_bwd_apply — also for hot rows, whose chunks are consecutive
         slices of the bucket folded in chunk order.  Needs the counters on the host: eager steps only (a debugging and
         regression-test mode; capture_step refuses it)."""
-        if torch.cuda.is_current_stream_capturing():
+        if plan.counters.is_cuda and torch.cuda.is_current_stream_capturing():
             raise RuntimeError('deterministic scatter mode reads the plan counters on the host: not capturable')
         nu, occ = int(plan.counters[0].item()), int(plan.counters[1].item())
         if nu == 0 or occ == 0:

@@ -27,7 +27,7 @@ extern "C" {
 #define ARX_E_UNSUPPORTED  -3
 #define ARX_E_CAPACITY     -4
 
-#define ARX_ABI_VERSION     3
+#define ARX_ABI_VERSION     4
 #define ARX_MAX_ATTRS      64
 
 /* One attribute (= one embedding table) of one entity side.  Mirrors the per-attribute

@@ -34,7 +34,7 @@ def test_binding_covers_every_declared_symbol():
 
 def test_abi_version_and_struct_layout():
     lib = _lib.load()
-    assert lib.arx_abi_version() == 3
+    assert lib.arx_abi_version() == 4
     assert ctypes.sizeof(_lib.AttrDesc) == 88      # 8 pointers + int64 + 2 x int32 + 1 pointer
     assert ctypes.sizeof(_lib.BwdPlan) == 112      # 11 pointers + 3 x int64
     assert b'sm_100a' in lib.arx_build_info()

@@ -1214,7 +1214,8 @@ class EmbeddingAttribute(object):
         if k not in self._side_streams:
             # (single-GPU step only: the row-sharded step keeps default priorities — its NCCL exchanges are part
             # of the captured graph and were validated at N = 2 / 4 with this scheduling)
-            prio = (0 if k >= 8 else -1) if self.shard is None else 0
+            # ... and the peer-memory step, whose graph holds no NCCL kernel: hmf/sharded.py sets use_priorities)
+            prio = (0 if k >= 8 else -1) if (self.shard is None or getattr(self, 'use_priorities', False)) else 0
             self._side_streams[k] = torch.cuda.Stream(device=self.device, priority=prio)
         return self._side_streams[k]
 

@@ -467,7 +467,7 @@ class LatentProductModel(object):
         self._g_items = items_dev.to(torch.int32).clone()
         self._g_loss_kind = loss
         self._g_lr = self.learning_rate.eval()
-        single = self.att_emb.shard is None
+        single = self.att_emb.shard is None or getattr(self.att_emb, 'use_priorities', False)
         # high priority on one GPU (see EmbeddingAttribute.side_stream); default streams for the sharded step
         side = torch.cuda.Stream(priority=-1) if single else torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())

@@ -263,6 +263,10 @@ class ShardedLatentProductModel(LatentProductModel):
                 print('[arecsys_b200] peer-memory exchange unavailable, using NCCL collectives: %s' % e, file=sys.stderr)
             self.px = None
             return False
+        # no NCCL kernel is left in the captured step: use the single-GPU scheduling (plan builds on low-priority
+        # streams, everything on the dependent chain — the barrier kernels above all — on high-priority ones)
+        self.att_emb.use_priorities = os.environ.get('ARX_PEER_PRIO', '1') == '1'
+        self.att_emb._side_streams = {}
         return True
 
     def _step_peer(self, users_g, items_g, mb, S, masks, sync):
@@ -273,6 +277,20 @@ class ShardedLatentProductModel(LatentProductModel):
         pre = m._out_prefix()
         f32 = dict(dtype=torch.float32, device=dev)
         px.clear_pool_gradients()                                   # before this step's first barrier
+        # nothing below depends on the lookups: the positives bit matrix and the zeroed outputs of the split accumulation
+        # are prepared on a side stream UNDER the lookups (forked here, before they are enqueued); they were 25 us of
+        # memsets + mask build on the dependent chain
+        users_l = users_g[r * mb:(r + 1) * mb].contiguous()
+        main = torch.cuda.current_stream()
+        side = m.side_stream(3)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            dU_z = torch.zeros((mb, d), **f32)
+            dPs_z = torch.zeros((S, d), **f32)
+            zb = torch.zeros((S + mb,), **f32)                      # dbs | dts
+            mwmask = m.mw_mask(mb, S, pos_rows=users_l)
+            ev_side = torch.cuda.Event()
+            ev_side.record(side)
         irng0 = m.sets[pre].attr_range()
         m.prefetch_plans({'user': [(m.sets['user'].attr_range(), users_g, POOL_MEAN)],
                           pre: [(irng0, m.sampled_ids, POOL_MEAN), (irng0, items_g, POOL_MEAN)]})
@@ -284,7 +302,6 @@ class ShardedLatentProductModel(LatentProductModel):
             (pre, m.sampled_ids, POOL_MEAN, True, {'push': px.push_desc('pool')})])
         px.barrier()                                                # B1: every rank's pushes have landed
         U0, Pt, btl, Ps, bsl = px.locU, px.locP, px.locb, px.spP, px.spb
-        users_l = users_g[r * mb:(r + 1) * mb].contiguous()
         keep = self.dropout
         scale = self._scale(n_g)[:mb]                               # 1 / (G*mb): global batch mean
         u = torch.empty((mb, d), **f32); U_r = torch.empty((mb, d), **f32); UT = torch.empty((d, mb), **f32)
@@ -307,11 +324,17 @@ class ShardedLatentProductModel(LatentProductModel):
         if drng is not None:
             dmask = dmask_out
         # fused_mw keeps no reference to Ps / bsl beyond its launches; they are read in place from the receive blocks
-        fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l, prepared=(U_r, P_r, UT, PT))
+        main.wait_event(ev_side)
+        fused = m.fused_mw(u, Ps, bsl, tscore, scale, True, pos_rows=users_l, prepared=(U_r, P_r, UT, PT), mask=mwmask,
+                           outputs=(dU_z, dPs_z, zb[:S], zb[S:]))
         if fused is None:
             raise RuntimeError('arx_mw_fwd / arx_mw_bwd rejected a shape ce_supported() accepted')
         bl, (dU, dPs, dbs, dts) = fused
-        loss_sum = (bl.sum() / n_g).reshape(1)
+        side.wait_stream(main)                                      # the scalar loss is off the dependent chain
+        with torch.cuda.stream(side):
+            loss_sum = (bl.sum() / n_g).reshape(1)
+            ev_loss = torch.cuda.Event()
+            ev_loss.record(side)
         dU0 = torch.empty((mb, d), **f32)
         dPt = torch.empty((mb, d), **f32)
         call('arx_mw_post', dU.data_ptr(), dts.data_ptr(), Pt.data_ptr(), u.data_ptr(), _lib.ptr(dmask), inv_keep, mb, d,
@@ -325,6 +348,7 @@ class ShardedLatentProductModel(LatentProductModel):
         m.push_grad(pre, rng, m.sampled_ids, POOL_MEAN, px.ig[:S], px.igb[:S])
         m.push_grad(pre, rng, items_g, POOL_MEAN, px.ig[S:], px.igb[S:])
         m.apply_gradients(self.learning_rate.eval(), OPT_ADAGRAD)
+        main.wait_event(ev_loss)
         self.global_step.assign(self.global_step.eval() + 1)
         if not sync:
             return loss_sum

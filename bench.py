@@ -76,21 +76,38 @@ class ClockSampler(object):
         self.idx = gpu_index
 
     def start(self):
+        self.skip = 0
+        if self.idx is None:
+            return
         try:
             self.p = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), '--query-gpu=' + self.Q,
-                                       '--format=csv,noheader,nounits', '-lms', '20'], stdout=self.f,
+                                       '--format=csv,noheader,nounits', '-lms', '25'], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
+    def mark(self):
+        """Forget the samples taken so far (warm-up): only what follows is reported."""
+        if self.p is None:
+            return
+        try:
+            self.skip = len([r for r in open(self.f.name).read().splitlines() if r.strip()])
+        except OSError:
+            self.skip = 0
+
     def stop(self):
         if self.p is None:
+            try:
+                os.unlink(self.f.name)
+            except OSError:
+                pass
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.p.terminate()
         self.p.wait()
         self.f.flush()
         rows = [r.strip().split(', ') for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        rows = rows[getattr(self, 'skip', 0):] or rows[-1:]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
@@ -308,7 +325,16 @@ def main():
             assert ok, 'sharded step disagrees with the single-GPU step: %r' % (sharded_check,)
         state['step'] += 1
         barrier()
+        if getattr(model, 'px', None) is not None:
+            cfg['parallelism'] = ('tables row-sharded x%d (row t on rank t %% N); pooled vectors and gradient rows exchanged '
+                                  'over NVLink peer memory from inside the kernels (lookup + reduce-scatter / all-reduce fused, '
+                                  'all-gather by push, two device-side barriers per step; ARX_PEER=0: NCCL collectives)' % world)
     # ---------------- value: ids resident in HBM ---------------------------------------
+    # The clock sampler (an nvidia-smi loop) is started BEFORE the warm-up steps and on rank 0 only: its start-up
+    # (process spawn + NVML initialisation, which takes driver-wide locks) used to land at the head of the timed window
+    # and, with one sampler per rank, stalled graph launches for 3-17 ms of a 15 ms window at N > 1.
+    clocks = ClockSampler(local_rank if rank == 0 else None)
+    clocks.start()
     for s in range(a.warmup):
         run_step(u_dev[s], i_dev[s], False)
     if use_graph:
@@ -316,8 +342,7 @@ def main():
         state['graph'] = True
         run_step(u_dev[1], i_dev[1], False)
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()                                              # samples from here on are "during the timed region"
     l0 = _lib.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -327,6 +352,8 @@ def main():
     barrier()
     launches = _lib.launch_count - l0
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1 and getattr(model, 'px', None) is not None:
+        model.px.check()                                       # the device-side barrier's watchdog never fired
     # ---------------- e2e: host ids -> H2D -> step -> loss D2H -------------------------
     # The training-loop form of the public API: every step copies its ids from pinned host memory, replays the
     # step and copies its loss back to the host; the host reads the loss one step late (replay_step(sync='lag')),

@@ -1,3 +1,4 @@
+# usage: bash tools/bench_multi_gpu.sh N "1 0"   -> bench.py on N GPUs with the peer-memory exchange (1) and / or the NCCL collectives (0); one-line summaries
 n=${1:-2}
 for peer in ${2:-1}; do
   ARX_PEER=$peer timeout -k 10 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$peer bench.py --gpus $n --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/r2_mg_n${n}_peer$peer.json 2> gpurun_out/r2_mg_n${n}_peer$peer.err

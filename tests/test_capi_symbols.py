@@ -63,3 +63,32 @@ def test_product_never_imports_the_oracle():
                     if re.search(r'^\s*(from|import)\s+oracle\b', src, re.M) or 'tf1_shim' in src:
                         offenders.append(os.path.join(dp, f))
     assert offenders == [], offenders
+
+
+def test_new_struct_layouts():
+    """arx_pool_push / arx_peer_seg as include/arx_b200.h declares them (the ctypes mirrors of INTEGRATION.md)."""
+    assert ctypes.sizeof(_lib.PoolPush) == 40      # 2 pointers + 2 x int64 + 2 x int32
+    assert ctypes.sizeof(_lib.PeerSeg) == 64       # 2 pointers + 5 x int64 + 2 x int32
+    assert ctypes.sizeof(_lib.PoolReq) == 56       # 4 pointers + 2 x int64 + 2 x int32
+
+
+def test_entry_points_reject_bad_arguments_before_touching_the_device():
+    """Argument validation comes first in every entry point, so it can be checked without a GPU: NULL pointers, sizes out
+    of range and unsupported modes return ARX_E_BADARG (-1) / ARX_E_UNSUPPORTED (-3), never a launch."""
+    lib = _lib.load()
+    plan = _lib.BwdPlan()                           # all-NULL plan
+    assert lib.arx_pool_bwd_apply_slab(None, 1, 128, plan, None, 0, None, 0.1, None, 0, 64, None) == -1
+    assert lib.arx_bwd_plan_alloc_h(None, plan, 64, None) == -1
+    assert lib.arx_peer_push_many(None, 1, 2, None) == -1
+    segs = (_lib.PeerSeg * 1)()
+    assert lib.arx_peer_push_many(ctypes.addressof(segs), 9, 2, None) == -1          # more than 8 segments
+    assert lib.arx_peer_push_many(ctypes.addressof(segs), 1, 2, None) == -1          # NULL source / destination
+    assert lib.arx_peer_barrier(None, 0, 2, None, 1000, None, None) == -1
+    assert lib.arx_peer_alloc(0, None) == -1
+    assert lib.arx_peer_export(None, None) == -1 and lib.arx_peer_open(None, None) == -1
+    assert lib.arx_pool_fwd_many_push(None, None, 1, 128, None) == -1
+    assert lib.arx_score_max(None, None, 1, 1, None, None) == -1
+    assert lib.arx_token_pool_fwd(None, None, 1, None, None, 1, 2, None, 1.0, None, None, None, None) == -1
+    assert lib.arx_rowsum(None, 1, 1, None, 0, None) == -1
+    assert lib.arx_set_tuning(b'heavy', 4) == -1 and lib.arx_set_tuning(b'no_such_knob', 1) == -1
+    assert lib.arx_set_tuning(b'heavy', 64) == 0

@@ -15,6 +15,7 @@ import pytest
 import arecsys_b200  # noqa: F401
 
 REF = '/root/reference'
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, 'utils')),
                                 reason='reference sources only exist in the authoring container')
 SHIM = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'tf1_shim')
@@ -448,3 +449,51 @@ def test_skipgram_pair_generator_matches_reference(py2):
         for step in range(30):
             ub, ib, ob = next(b)
             assert np.array_equal(ra[step][0], ub) and np.array_equal(ra[step][1], ib[0]) and np.array_equal(ra[step][2], ob), (mb, step)
+
+
+def _flag_table(path, prefix):
+    """name -> (kind, default literal) of every DEFINE_<kind>("name", default, ...) in a launcher."""
+    import ast
+    import re
+    src = open(path).read()
+    out = {}
+    for m in re.finditer(re.escape(prefix) + r'DEFINE_(\w+)\(\s*"([^"]+)"\s*,\s*', src):
+        kind, name = m.group(1), m.group(2)
+        if '#' in src[src.rfind('\n', 0, m.start()) + 1:m.start()]:
+            continue                                # a commented-out definition
+        rest = src[m.end():]
+        depth, i, in_s = 0, 0, None                 # default = text up to the next top-level comma
+        while i < len(rest):
+            c = rest[i]
+            if in_s:
+                if c == '\\':
+                    i += 1
+                elif c == in_s:
+                    in_s = None
+            elif c in '"\'':
+                in_s = c
+            elif c in '([{':
+                depth += 1
+            elif c in ')]}':
+                if depth == 0:
+                    break
+                depth -= 1
+            elif c == ',' and depth == 0:
+                break
+            i += 1
+        out[name] = (kind, ast.literal_eval(rest[:i].strip()))
+    return out
+
+
+@pytest.mark.parametrize('launcher', ['hmf/run_hmf.py', 'lstm/run.py', 'word2vec/run_w2v.py'])
+def test_launcher_flag_surface_matches_reference(launcher):
+    """every flag of the reference's launcher exists here with the same type and the same default, so that
+    examples/run_hmf.sh / run_lstm.sh / run_w2v.sh drive this repo's launchers unchanged.  Flags this repo adds must be
+    additions only (max_steps and the like)."""
+    ref = _flag_table(os.path.join(REF, launcher), 'tf.app.flags.')
+    ours = _flag_table(os.path.join(ROOT, launcher), 'FLAGS.')
+    assert len(ref) >= 35
+    missing = sorted(set(ref) - set(ours))
+    assert not missing, 'reference flags this launcher does not define: %s' % missing
+    diff = {k: (ref[k], ours[k]) for k in ref if ref[k] != ours[k]}
+    assert not diff, 'type / default differs from the reference: %s' % diff

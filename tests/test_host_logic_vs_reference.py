@@ -497,3 +497,24 @@ def test_launcher_flag_surface_matches_reference(launcher):
     assert not missing, 'reference flags this launcher does not define: %s' % missing
     diff = {k: (ref[k], ours[k]) for k in ref if ref[k] != ours[k]}
     assert not diff, 'type / default differs from the reference: %s' % diff
+
+
+@pytest.mark.parametrize('launcher,dead', [
+    ('hmf/run_hmf.py', ()),
+    # the ensemble driver is dead code in the reference, iteType is hard-wired to 0 (lstm/run.py:418)
+    ('lstm/run.py', ('Ensemble {} {}', 'Ensembling n {}', 'Loading results from {}', 'withSequence')),
+    ('word2vec/run_w2v.py', ())])
+def test_launcher_log_lines_match_reference(launcher, dead):
+    """tools that parse log.txt (perplexity / loss / dev lines, METRIC_FORMAT) keep working — every
+    format string the reference's launcher passes to mylog() appears verbatim in this repo's launcher."""
+    import re
+    ref = open(os.path.join(REF, launcher)).read()
+    ours = open(os.path.join(ROOT, launcher)).read()
+    lits = set()
+    for m in re.finditer(r'mylog\(\s*(["\'])(.*?)\1', ref):
+        if '#' in ref[ref.rfind('\n', 0, m.start()) + 1:m.start()]:
+            continue
+        lits.add(m.group(2))
+    assert len(lits) >= 20
+    missing = sorted(x for x in lits if x not in ours and x not in dead)
+    assert not missing, missing

@@ -177,7 +177,7 @@ def train(raw_data=None):
     step_time, loss, current_step = 0.0, 0.0, 0
     patience = FLAGS.patience
     previous_losses, losses_dev = [], []
-    best_loss = 1000000
+    best_auc, best_loss = -1, 1000000                                         # run_w2v.py:284 (the auc is never computed)
     item_sampled, item_sampled_id2idx = None, None
     train_total_size = float(len(data_tr))
     steps_per_epoch = int(1.0 * train_total_size / FLAGS.batch_size)
@@ -193,6 +193,15 @@ def train(raw_data=None):
     while True:
         start_time = time.time()
         (user_input, input_items, output_items) = next(ite)
+        if current_step < 5:                                                  # run_w2v.py:305-312: the first batches, verbatim
+            as_list = lambda x: x.tolist() if hasattr(x, 'tolist') else x
+            mylog("current step is {}".format(current_step))
+            mylog('user')
+            mylog(as_list(user_input))
+            mylog('input_item')
+            mylog(as_list(input_items))
+            mylog('output_item')
+            mylog(as_list(output_items))
         if FLAGS.loss in ['mw', 'mce'] and current_step % FLAGS.n_resample == 0:
             item_sampled, item_sampled_id2idx = sample_items(item_population, FLAGS.n_sampled, p_item)
         else:
@@ -257,6 +266,7 @@ def train(raw_data=None):
             losses_dev.append(eval_loss)
             if patience < 0 and not FLAGS.test:
                 mylog("no improvement for too long.. terminating..")
+                mylog("best auc %.4f" % best_auc)
                 mylog("best loss %.4f" % best_loss)
                 sys.stdout.flush()
                 break

@@ -26,7 +26,10 @@ class DataIterator(object):
 
     def next_sequence(self, stop=False, recommend=False):
         """Deterministic sweep: every bucket in order, consecutive windows of batch_size sequences until the
-        batch builder reports the bucket exhausted; one pass when `stop`, else round and round."""
+        batch builder reports the bucket exhausted; one pass when `stop`, else round and round.  Deliberate difference
+        from lstm/data_iterator.py:22-42: an EMPTY bucket is skipped, where the reference issues one all-padding batch
+        (zero weights: it adds nothing to a loss or a recommendation, only a kernel launch); pinned by
+        tests/test_host_logic_vs_reference.py::test_lstm_data_iterator_streams_match_reference."""
         fetch = self.model.get_batch_recommend if recommend else self.model.get_batch
         while True:
             for b in range(self.n_bucket):

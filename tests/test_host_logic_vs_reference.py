@@ -567,3 +567,26 @@ def test_lstm_data_iterator_streams_match_reference(py2):
         a = [next(ga)[4] for _ in range(40)]
         b = [next(gb)[4] for _ in range(40)]
         assert [x for x in a if sizes[x] > 0][:25] == b[:25]
+
+
+def test_bucket_boundaries_match_reference(py2):
+    """lstm/best_buckets.py::calculate_buckets.  The file holds Python-2 print statements, so it cannot be imported;
+    the test executes its source with those statements blanked (nothing else touched) and compares the bucket
+    boundaries with this repo's function over random length distributions."""
+    import re
+    src = open(os.path.join(REF, 'lstm', 'best_buckets.py')).read()
+    src = src[:src.index('def main')]                                   # the function only; main() is a demo
+    src = re.sub(r'^(\s*)print [^\n(][^\n]*$', r'\1pass', src, flags=re.M)
+    ns = {}
+    exec(compile(src, 'ref_best_buckets', 'exec'), ns)
+    from arecsys_b200.lstm.best_buckets import calculate_buckets as ours
+    rng = np.random.default_rng(0)
+    for trial in range(40):
+        n = int(rng.integers(1, 400))
+        top = int(rng.integers(2, 90))
+        lens = np.minimum(1 + rng.geometric(0.08, n), top) if trial % 2 else rng.integers(1, top + 1, n)
+        array = [(int(u), list(range(int(l)))) for u, l in enumerate(lens)]
+        for L, nb in ((10, 3), (30, 4), (100, 8), (50, 1), (5, 10)):
+            a = ns['calculate_buckets'](array, L, nb)
+            b = ours(array, L, nb)
+            assert sorted(a) == sorted(b), (trial, L, nb, a, b)
